@@ -1,0 +1,277 @@
+#!/usr/bin/env python3
+"""Benchmark of the wave-propagation hot path (BASELINE.json metric: node-updates/s and % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one fused leapfrog pass over the whole lattice (every node updated once).
+Workloads (config.workload):
+  cfg2-2d-8192      BASELINE configs[1]: 2-D tetrakis 8192x8192, no defect, fp64   (default at N=1)
+  cfg3-slab-1024x64 BASELINE configs[2] shape: 3-D 1024x1024, 64 layers PER GPU, black hole r=64 at the
+                    global centre, layer slabs + halo exchange over NCCL            (default at N>1)
+Prints ONE JSON line (rank 0).  `value` is device-timed with the state resident in HBM; `e2e` is the same
+metric through the C ABI with host buffers (kicks H2D, probe series + final state D2H inside the timed
+region); `roofline` is the step kernel's algorithmic bytes / its CUDA-event time against the measured HBM
+peak; `cpu_baseline` is the oracle (oracle/wave_oracle.c, OpenMP) on this box's host cores.
+`--impl reference` times that CPU restatement alone (the reference itself is pure Python over networkx and
+cannot even build these lattices: 2.2e12 edges for cfg2 -- BASELINE.md section 1).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "node-updates/sec"
+UNIT = "GNUPS"
+BYTES_PER_UPDATE = 24.0  # read u_t, read u_{t-1}, write u_{t+1}; fp64
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C/OpenMP clique-sum restatement on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------------
+def cpu_run(workload: str, steps: int, warmup: int, budget_s: float):
+    from oracle import wave_oracle as wo
+
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    three_d = workload.startswith("cfg3")
+
+    def shape(size):
+        return (size, 16) if three_d else (size, 1)
+
+    def one(size, nsteps):
+        S, L = shape(size)
+        u0 = np.zeros(L * S * S * 4)
+        u0[((L // 2 * S + S // 2) * S + S // 2) * 4] = 1.0
+        maxdeg = 3 + 2 * (S - 1) + (2 if L > 1 else 0)
+        coeff = 1.0 / maxdeg  # dt at the CFL limit, c = 1
+        t0 = time.perf_counter()
+        wo.run_structured(S, L, None, None, None, [], u0, nsteps, coeff, 0.0)
+        return time.perf_counter() - t0, L * S * S * 4
+
+    t, n = one(256, 4)  # calibrate seconds per node-update
+    per_nu = max(t / (4 * n), 1e-12)
+    size = 256
+    for cand in (512, 1024, 2048, 4096):
+        S, L = shape(cand)
+        if (steps + warmup) * L * cand * cand * 4 * per_nu <= budget_s:
+            size = cand
+    if warmup:
+        one(size, warmup)
+    t, n = one(size, steps)
+    S, L = shape(size)
+    sample = (f"{'3-D' if three_d else '2-D'} tetrakis {S}x{S}" + (f"x{L}" if three_d else "") +
+              f" no defect, {steps} steps, oracle/wave_oracle.c clique-sum restatement, OpenMP {cores} threads")
+    return {"value": n * steps / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "seconds": t, "ms_per_step": 1e3 * t / max(steps, 1)}
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return 0
+    workload = args.workload or ("cfg2-2d-8192" if args.gpus == 1 else "cfg3-slab-1024x64")
+    res = cpu_run(workload, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": workload, "sample": res["sample"]},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def pinned_empty(n):
+    import torch
+
+    t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    return t, t.numpy()
+
+
+def gpu_single(args):
+    import torch
+
+    import tetrakis_sim_b200 as tk
+
+    torch.cuda.init()
+    workload = args.workload or "cfg2-2d-8192"
+    if workload == "cfg2-2d-8192":
+        spec = tk.LatticeSpec(size=args.size or 8192, dim=2)
+        dt_req, desc = 0.1, "2-D tetrakis {0}x{0}, no defect, fp64, kick (S/2,S/2,'A'), dt 0.1 -> CFL-clamped"
+    elif workload == "cfg3-slab-1024x64":
+        spec = tk.LatticeSpec(size=args.size or 1024, dim=3, layers=args.layers or 64, defect="blackhole",
+                              radius=64.0)
+        dt_req, desc = 0.1, "3-D tetrakis {0}x{0}x" + str(spec.layers) + ", black hole r=64 at the centre, fp64"
+    elif workload == "cfg4-3d-512":
+        spec = tk.LatticeSpec(size=args.size or 512, dim=3, layers=args.layers or 512, defect="singularity",
+                              radius=2.5, mass=2000.0, prune_edges=True)
+        dt_req, desc = 0.1, "3-D tetrakis {0}^3 singularity mass 2000 + prune_edges, fp64"
+    else:
+        raise SystemExit(f"unknown workload {workload}")
+    desc = desc.format(spec.size)
+    kick = spec.kick_node() if spec.defect != "none" else spec.bench_kick_node()
+    plan = tk.compile_lattice(spec, device=0)
+    maxdeg = plan.max_degree
+    limit = 1.0 / np.sqrt(maxdeg)
+    dt_eff = min(dt_req, limit)
+    coeff = dt_eff ** 2
+    n_updates = spec.num_nodes  # surviving nodes
+    kidx = [spec.index(kick)]
+
+    plan.set_state_sparse(kidx, [1.0])
+    plan.run(args.warmup, coeff, 0.0, probes=kidx)
+    torch.cuda.synchronize()
+    l0 = plan.launches
+    with ClockSampler(0) as clk:
+        out = plan.run(args.steps, coeff, 0.0, probes=kidx, timed=True)
+        torch.cuda.synchronize()
+    launches = plan.launches - l0
+    ms = out["elapsed_ms"]
+    kms = out["step_kernel_ms"]
+    value = n_updates * args.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak_gbs()
+    achieved = n_updates * BYTES_PER_UPDATE * args.steps / (kms * 1e-3) / 1e9
+    checksum = float(plan.get_state().sum()) if spec.num_slots <= 600_000_000 else None
+
+    # e2e: the whole run through the C ABI with host buffers (kicks H2D; probe series and the final
+    # state D2H into pinned host memory), device-synchronised wall clock
+    hold, final = pinned_empty(plan.num_nodes)
+    from tetrakis_sim_b200 import _lib
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan.set_state_sparse(kidx, [1.0])
+    o2 = plan.run(args.steps, coeff, 0.0, probes=kidx)
+    _lib.check(_lib.lib().tk_plan_get_state(plan._h, _lib._p(final), None))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": n_updates * args.steps / e2e_s / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": 16.0 / args.steps,
+           "d2h_bytes_per_step": (final.nbytes + o2["probes"].nbytes) / args.steps,
+           "seconds": e2e_s, "includes": "set_state_sparse + run + probe series D2H + final state D2H (pinned)"}
+    plan.close()
+
+    cpu = cpu_run(workload, steps=10, warmup=1, budget_s=15.0) if not args.no_cpu else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "lattice": desc, "nodes": n_updates, "max_degree": maxdeg,
+                   "effective_dt": dt_eff, "kick": list(map(str, kick)),
+                   "l2": f"state {2 * spec.num_slots * 8 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
+                   "kernel_variant": {k: os.environ.get(k) for k in ("TK_LAT_CPL", "TK_LAT_WC", "TK_LAT_RCHUNK")
+                                      if os.environ.get(k)}},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "lat_step_kernel", "bytes_per_update": BYTES_PER_UPDATE,
+                     "kernel_ms_per_launch": kms / args.steps,
+                     "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0},
+        "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
+        # sum_i u_t(i) = 1 + t for unit masses (zero column sums of the Laplacian): a whole-lattice checksum
+        "checksum_sum_u": checksum,
+        "checksum_expected": float(args.warmup + args.steps + 1) if spec.defect != "singularity" else None,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--layers", type=int, default=None)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        return gpu_single(args)
+    from tetrakis_sim_b200.slab import bench_slabs  # multi-GPU: layer slabs + halo exchange
+
+    return bench_slabs(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,159 @@
+/*
+ * tetrakis_b200.h -- C ABI of the B200-native wave-propagation hot path of tetrakis-sim.
+ *
+ * The reference (pure Python) has no FFI layer; its boundary for this path is two functions,
+ *     tetrakis_sim.physics.run_wave_sim   (reference tetrakis_sim/physics.py:41-131)
+ *     tetrakis_sim.physics.run_fft        (reference tetrakis_sim/physics.py:140-165)
+ * This header is what a ctypes / cffi / CPython-extension binding inside those two functions
+ * would call (INTEGRATION.md shows the stub).  Plain pointers and sizes only; every function
+ * returns an int status (TK_OK == 0) and leaves a message for tk_last_error() on failure.
+ *
+ * Ownership: caller owns every host buffer passed in or out; the library owns all device
+ * memory, released by tk_plan_destroy().  A plan is bound to one device and one stream and is
+ * not thread-safe; distinct plans are independent.  There is NO CPU fallback: every entry point
+ * that computes fails with TK_ERR_NO_DEVICE when no CUDA device is present.
+ *
+ * Node numbering
+ *   graph plans   : 0..n-1 in list(G.nodes) order (physics.py:56).
+ *   lattice plans : linear index ((z*size + r)*size + c)*4 + q, q = 0..3 for "ABCD"; the
+ *                   reference's (r,c[,z],q) tuples (lattice.py:30,48-54) map onto it.  A plan that
+ *                   owns the slab [z_begin, z_end) uses LOCAL indices with z relative to z_begin.
+ */
+#ifndef TETRAKIS_B200_H
+#define TETRAKIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TK_ABI_VERSION 1
+
+#define TK_OK 0
+#define TK_ERR_INVALID 1   /* bad argument */
+#define TK_ERR_CUDA 2      /* CUDA runtime error (message has the cudaError string) */
+#define TK_ERR_NOMEM 3     /* host or device allocation failed */
+#define TK_ERR_NO_DEVICE 4 /* no usable CUDA device: there is no CPU path */
+
+typedef struct tk_plan tk_plan;
+
+int tk_abi_version(void);
+/* Thread-local, NUL-terminated description of the last failure on this thread. */
+const char *tk_last_error(void);
+int tk_device_count(int *count);
+int tk_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major,
+                   int *cc_minor, int64_t *total_mem_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph plan: any networkx graph.  Replaces the per-call precompute of physics.py:56-64,93-102
+ * (node list, degrees, neighbour lists, inv_mass, potential).  Neighbours are summed in the
+ * order given (adjacency order), which makes the device result bit-identical to the reference.
+ *   rowptr[n+1], colidx[rowptr[n]] : neighbour lists (list(G[n]), physics.py:94)
+ *   degree[n]                      : G.degree (physics.py:60-62; self-loops count twice)
+ *   inv_mass[n], potential[n]      : physics.py:97-102 (mass <= 0 -> 1 is the caller's job)
+ * ------------------------------------------------------------------------------------------ */
+int tk_graph_plan_create(int device, int64_t n_nodes, const int64_t *rowptr,
+                         const int32_t *colidx, const double *degree, const double *inv_mass,
+                         const double *potential, tk_plan **out);
+
+/* ------------------------------------------------------------------------------------------
+ * Lattice plan: a tetrakis sheet (lattice.py:15-76) described by its shape plus the sparse set
+ * of nodes / edges that a defect (defects.py) changed.  Nothing O(N) crosses the ABI.
+ *   special_* : nodes that are removed, edge-pruned or carry a mass/potential tag
+ *       special_index  GLOBAL linear index (z over all `layers`)
+ *       special_flags  bit0 alive (0 = removed, defects.py:133), bit1 part (0 = all incident
+ *                      edges pruned, defects.py:227-232)
+ *       special_inv_mass / special_potential  physics.py:97-102 values for that node
+ *   corr_*    : directed edge corrections relative to the clique model; node a gains
+ *               sign*u[b] in its neighbour sum and sign in its degree (wedge: two entries with
+ *               sign -1 for the A-B edge, defects.py:78-81,97-103).  GLOBAL indices.
+ *   [z_begin, z_end) : the slab of layers this plan owns (0, layers for a single GPU).  One halo
+ *               plane is kept on each side; see tk_lattice_halo_ptrs.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tk_lattice_desc {
+    int32_t size;   /* cells per side */
+    int32_t layers; /* total layers; 1 for a 2-D sheet */
+    int32_t z_begin;
+    int32_t z_end;
+    int64_t n_special;
+    const int64_t *special_index;
+    const uint8_t *special_flags;
+    const double *special_inv_mass;
+    const double *special_potential;
+    int64_t n_corr;
+    const int64_t *corr_a;
+    const int64_t *corr_b;
+    const double *corr_sign;
+} tk_lattice_desc;
+
+int tk_lattice_plan_create(int device, const tk_lattice_desc *desc, tk_plan **out);
+
+/* ------------------------------------------------------------------------------------------
+ * Common plan API
+ * ------------------------------------------------------------------------------------------ */
+/* Run on an existing cudaStream_t (e.g. torch's current stream) instead of the plan's own. */
+int tk_plan_set_stream(tk_plan *plan, void *cuda_stream);
+/* Local node count (lattice plans: owned planes only, removed nodes included). */
+int tk_plan_num_nodes(const tk_plan *plan, int64_t *n);
+/* max G.degree over existing nodes (physics.py:64) -- input of the CFL clamp (physics.py:74-91). */
+int tk_plan_max_degree(tk_plan *plan, int64_t *max_degree);
+/* u <- 0, u_prev <- 0 (physics.py:58), then u[index[i]] = value[i] (physics.py:30-38). */
+int tk_plan_set_state_sparse(tk_plan *plan, int64_t n, const int64_t *index, const double *value);
+/* Dense host -> device; u_prev may be NULL (zeros).  Values at removed nodes are forced to 0. */
+int tk_plan_set_state(tk_plan *plan, const double *u, const double *u_prev);
+/* Dense device -> host; either pointer may be NULL. */
+int tk_plan_get_state(tk_plan *plan, double *u, double *u_prev);
+
+typedef struct tk_run_args {
+    int64_t steps;
+    double coeff;   /* (c * effective_dt)^2, physics.py:105 */
+    double damping; /* physics.py:125 */
+    int64_t n_probes;
+    const int64_t *probe_index; /* local node indices */
+    double *probe_out;          /* host, (steps+1) x n_probes, row 0 = state before the first step */
+    double *history_out;        /* host or NULL, (steps+1) x num_nodes (physics.py:104,129) */
+    double *energy_out;         /* host or NULL, (steps+1): discrete energy (not in the reference) */
+    double *elapsed_ms;         /* host or NULL: device time of the stepping loop (CUDA events) */
+    double *step_kernel_ms;     /* host or NULL: summed CUDA-event time of the step kernels alone */
+} tk_run_args;
+
+/* physics.py:106-129: `steps` leapfrog updates, synchronous.  The state stays on the device, so
+ * consecutive calls continue the same simulation. */
+int tk_plan_run(tk_plan *plan, const tk_run_args *args);
+
+/* Kernel launches issued by this plan since creation (bench.py's gpu_launches). */
+int tk_plan_launch_count(const tk_plan *plan, int64_t *launches);
+int tk_plan_destroy(tk_plan *plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Slab stepping for multi-GPU runs (one process per GPU; the halo exchange itself is done by
+ * the caller with NCCL / peer copies between the two phase calls).  All asynchronous on the
+ * plan's stream.
+ * ------------------------------------------------------------------------------------------ */
+/* Device addresses of the four planes involved in a halo exchange: send_lo/send_hi = first/last
+ * owned plane, recv_lo/recv_hi = halo below/above; plane_bytes = size*size*4*8.
+ * next_state = 0: planes of the current state u_t; 1: planes of the buffer the running step
+ * writes u_{t+1} into (so the exchange can start as soon as the boundary layers are updated and
+ * overlap the interior layers).  The two buffers alternate at every tk_lattice_step_end. */
+int tk_lattice_halo_ptrs(tk_plan *plan, int32_t next_state, void **send_lo, void **send_hi,
+                         void **recv_lo, void **recv_hi, int64_t *plane_bytes);
+/* Prepare a run: zero the probe cursor, compute the row/column sums of the current state. */
+int tk_lattice_step_begin(tk_plan *plan, double coeff, double damping);
+/* Update local layers [zl_begin, zl_end) (reads the current halos). */
+int tk_lattice_step_layers(tk_plan *plan, int32_t zl_begin, int32_t zl_end);
+/* After every layer was updated: finish the row/column sums of the new state, swap buffers. */
+int tk_lattice_step_end(tk_plan *plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Probe spectrum: |DFT| of `batch` real series of length n (physics.py:162-163, np.fft.fft of a
+ * real signal; n is arbitrary, steps+1 is never a power of two) and np.argmax of each
+ * (batch.py:205).  series: batch x n, spectrum: batch x n, argmax: batch (may be NULL).
+ * ------------------------------------------------------------------------------------------ */
+int tk_dft_abs(int device, const double *series, int64_t batch, int64_t n, double *spectrum,
+               int64_t *argmax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETRAKIS_B200_H */

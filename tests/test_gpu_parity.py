@@ -1,0 +1,242 @@
+"""GPU parity tests proper: the CUDA path, called through the drop-in API / C ABI, against the
+golden vectors generated from the unmodified reference and against the oracle.
+
+Bars: generic-graph kernel BIT-EXACT on u(t); structured kernel within
+1e-10 relative (inf-norm over all nodes and steps, relative to max|u_ref|; we hold 1e-12 at <= 100
+steps); dominant-frequency bin identical modulo the k <-> N-k mirror.
+"""
+
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import tetrakis_sim_b200 as tk
+from oracle import wave_oracle as wo
+from tests.helpers import golden_names, graph_from_golden, lattice_names, load_golden, rel_inf
+from tests.test_cpu_host import _spec_from
+
+pytestmark = pytest.mark.gpu
+
+
+def _initial_data(g, labels):
+    nz = np.flatnonzero(g["u0"])
+    return {labels[i]: float(g["u0"][i]) for i in nz}
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_graph_kernel_is_bit_exact_with_the_reference(name):
+    g = load_golden(name)
+    G, labels = graph_from_golden(g)
+    if name == "random_graph_multi_kick":
+        G.add_edge(5, 5)  # restore the self-loop's degree contribution (adjacency unchanged)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        hist = tk.run_wave_sim(G, steps=g["steps"], initial_data=_initial_data(g, labels),
+                               c=g["c"], dt=g["dt"], damping=g["damping"])
+    assert [str(w.message) for w in caught if w.category is RuntimeWarning] == g["warning"]
+    assert isinstance(hist, tk.SimulationHistory) and len(hist) == g["steps"] + 1
+    assert hist.dt == g["effective_dt"]
+    assert {k: float(v) for k, v in hist.metadata.items()} == {k: float(v) for k, v in g["metadata"].items()}
+    assert np.array_equal(hist.array[g["snap_steps"]], g["states"])
+    probe = labels[g["probe_index"]]
+    assert [s[probe] for s in hist] == g["probe_values"].tolist()
+    assert list(hist[0].keys()) == labels
+    freq, spectrum, values = tk.run_fft(hist, probe)
+    assert np.array_equal(values, g["probe_values"]) and np.array_equal(freq, g["fft_freq"])
+    assert rel_inf(spectrum, g["fft_spectrum"]) < 1e-12
+    assert wo.folded_bin(spectrum) == wo.folded_bin(g["fft_spectrum"])
+    assert abs(tk.dominant_frequency(freq, spectrum)) == pytest.approx(abs(g["dominant_freq"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("name", lattice_names())
+@pytest.mark.parametrize("route", ["spec", "graph"])
+def test_structured_kernel_matches_the_reference(name, route):
+    g = load_golden(name)
+    lat = g["lattice"]
+    tol = 1e-12 if g["steps"] <= 100 else 1e-10
+    G, labels = graph_from_golden(g)
+    init = _initial_data(g, labels)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        if route == "graph":
+            hist = tk.run_wave_sim(G, steps=g["steps"], initial_data=init, c=g["c"], dt=g["dt"],
+                                   damping=g["damping"], path="structured")
+            states = hist.array[g["snap_steps"]]
+        else:
+            spec = _spec_from(lat)
+            probe = labels[g["probe_index"]]
+            hist = tk.run_wave_sim(spec, steps=g["steps"], initial_data=init, c=g["c"], dt=g["dt"],
+                                   damping=g["damping"], record="all", probes=[probe])
+            idx = np.array([spec.index(n) for n in labels])
+            states = hist.array[g["snap_steps"]][:, idx]
+            dead = np.setdiff1d(np.arange(spec.num_slots), idx)
+            assert not hist.array[:, dead].any(), "removed nodes must stay at 0"
+            assert rel_inf(hist.probe_series[:, 0], g["probe_values"]) < tol
+            freq, spectrum, _ = tk.run_fft(hist, probe)
+            assert wo.folded_bin(spectrum) == wo.folded_bin(g["fft_spectrum"])
+            assert rel_inf(spectrum, g["fft_spectrum"]) < 10 * tol
+    assert hist.dt == g["effective_dt"]
+    assert hist.metadata["max_degree"] == g["metadata"]["max_degree"]
+    assert rel_inf(states, g["states"]) < tol
+
+
+VARIANTS = [(1, 8, 16), (1, 2, 32), (1, 1, 64), (2, 8, 16), (2, 2, 32), (2, 1, 256), (4, 8, 32), (4, 1, 16)]
+
+
+@pytest.mark.parametrize("cpl,wc,rchunk", VARIANTS)
+@pytest.mark.parametrize("case", ["2d_hole", "3d_sing", "3d_wedge_odd"])
+def test_every_kernel_variant_against_the_oracle(cpl, wc, rchunk, case, monkeypatch):
+    """Medium lattices (several segments, ragged tails, many row chunks) vs the C oracle."""
+    monkeypatch.setenv("TK_LAT_CPL", str(cpl))
+    monkeypatch.setenv("TK_LAT_WC", str(wc))
+    monkeypatch.setenv("TK_LAT_RCHUNK", str(rchunk))
+    if case == "2d_hole":
+        spec = tk.LatticeSpec(size=150, dim=2, defect="blackhole", radius=9.3, center=(70, 66))
+        steps, damping = 30, 0.01
+    elif case == "3d_sing":
+        spec = tk.LatticeSpec(size=70, dim=3, layers=11, defect="singularity", radius=3.0,
+                              mass=2000.0, potential=1.5, prune_edges=True)
+        steps, damping = 20, 0.0
+    else:
+        spec = tk.LatticeSpec(size=37, dim=3, layers=9, defect="wedge")
+        steps, damping = 25, 0.02
+    kick = spec.kick_node()
+    far = spec.node(spec.index(kick) ^ 3)
+    flags = np.full(spec.num_slots, 3, dtype=np.uint8)
+    im = np.ones(spec.num_slots)
+    pot = np.zeros(spec.num_slots)
+    si, sf, sm, sv = spec.specials()
+    flags[si], im[si], pot[si] = sf, sm, sv
+    u0 = np.zeros(spec.num_slots)
+    u0[spec.index(kick)] = 1.0
+    u0[spec.index(far)] = -0.25
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        hist = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0, far: -0.25}, c=1.0,
+                               dt=0.05, damping=damping, probes=[kick, far])
+    coeff = (1.0 * hist.dt) ** 2
+    ref = wo.run_structured(spec.size, spec.layers, flags, im, pot, spec.corrections(), u0, steps,
+                            coeff, damping, probes=[spec.index(kick), spec.index(far)])
+    assert rel_inf(hist.final_state, ref["u"]) < 1e-12
+    assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
+
+
+def test_structured_and_graph_kernels_agree_on_a_medium_singularity_lattice():
+    """SURVEY.md 8d config 4 cross-check: structured vs sliced-ELL on the same operator."""
+    from oracle import lattice_oracle as lo
+
+    G, _, center = lo.build_case(24, 3, 6, "singularity", radius=2.5, mass=2000.0, prune_edges=True)
+    kick = lo.pick_kick_node(G, center, 3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        a = tk.run_wave_sim(G, steps=60, initial_data={kick: 1.0}, dt=0.2)
+        b = tk.run_wave_sim(G, steps=60, initial_data={kick: 1.0}, dt=0.2, path="structured")
+        spec = tk.LatticeSpec(size=24, dim=3, layers=6, defect="singularity", radius=2.5,
+                              mass=2000.0, prune_edges=True)
+        c = tk.run_wave_sim(spec, steps=60, initial_data={kick: 1.0}, dt=0.2, record="all")
+    assert spec.kick_node() == kick
+    assert rel_inf(b.array, a.array) < 1e-12
+    idx = np.array([spec.index(n) for n in a.nodes])
+    assert rel_inf(c.array[:, idx], a.array) < 1e-12
+    assert a.metadata == b.metadata
+    assert {k: v for k, v in c.metadata.items() if k != "launches"} == a.metadata
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 51, 64, 1000, 10001])
+def test_device_dft_matches_numpy_fft(n):
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=n) + np.sin(np.arange(n) * 0.37)
+    spec, arg = tk.dft_abs(x)
+    ref = np.abs(np.fft.fft(x))
+    assert rel_inf(spec, ref) < 1e-12
+    assert wo.folded_bin(spec) == wo.folded_bin(ref) and spec[arg] == spec.max()
+    xb = rng.normal(size=(5, n))
+    sb, ab = tk.dft_abs(xb)
+    assert rel_inf(sb, np.abs(np.fft.fft(xb, axis=1))) < 1e-12 and ab.shape == (5,)
+
+
+def test_run_fft_reference_contract():
+    """tests/test_physics.py:30-38 and tests/test_invariants.py:96-115 of the reference."""
+    h = tk.SimulationHistory([{0: 0.0}, {0: 1.0}, {0: 0.0}, {0: -1.0}], dt=0.5, wave_speed=1.0)
+    freq, spectrum, values = tk.run_fft(h, node=0)
+    assert np.allclose(values, [0.0, 1.0, 0.0, -1.0]) and freq[1] == pytest.approx(0.5)
+    assert np.argmax(spectrum) in (1, 3)
+    t = np.arange(100) * 0.1
+    h = tk.SimulationHistory([{0: float(v)} for v in np.sin(2 * np.pi * 2.0 * t)], dt=0.1, wave_speed=1.0)
+    freq, spectrum, _ = tk.run_fft(h, node=0)
+    assert abs(abs(float(freq[int(np.argmax(spectrum))])) - 2.0) <= 0.1 + 1e-9
+    with pytest.raises(ValueError, match="empty"):
+        tk.run_fft([])
+
+
+def test_reference_behavioural_contract_small_graphs():
+    """The reference's own unit tests for this path, run against the drop-in
+    (tests/test_physics.py:19-27, test_physics_mass_potential.py, test_invariants.py:66-93)."""
+    import math
+
+    import networkx as nx
+
+    with pytest.warns(RuntimeWarning, match="Clamping dt"):
+        h = tk.run_wave_sim(nx.path_graph(3), steps=3, c=1.0, dt=5.0)
+    assert h.dt == pytest.approx(1 / math.sqrt(2)) and h.metadata["stability_adjusted"] is True
+    assert h.metadata["max_degree"] == 2
+
+    def one_step(**attrs):
+        G = nx.Graph()
+        G.add_edge(0, 1)
+        G.nodes[0].update(attrs)
+        return tk.run_wave_sim(G, steps=1, initial_data={0: 1.0}, c=1.0, dt=0.1)[-1][0]
+
+    assert one_step(mass=10.0) > one_step() > one_step(potential=2.0)
+    from oracle import lattice_oracle as lo
+
+    G = lo.build_sheet(size=3, dim=2)
+    with pytest.warns(RuntimeWarning, match=r"Clamping dt"):
+        h = tk.run_wave_sim(G, steps=25, c=1.0, dt=10.0, damping=0.0)
+    vals = np.asarray([v for s in h for v in s.values()])
+    assert np.isfinite(vals).all() and np.max(np.abs(vals)) < 1e3
+    assert h.metadata["stability_limit"] == pytest.approx(1 / math.sqrt(h.metadata["max_degree"]))
+    # empty graph, zero steps, kick on a node that is not in the graph
+    assert len(tk.run_wave_sim(nx.Graph(), steps=3)) == 4
+    h = tk.run_wave_sim(nx.path_graph(4), steps=0, initial_data={"ghost": 2.0, 1: 0.5})
+    assert len(h) == 1 and h[0]["ghost"] == 2.0 and h[0][1] == 0.5
+    assert G.number_of_edges() == lo.build_sheet(size=3, dim=2).number_of_edges()  # not mutated
+
+
+def test_size_independent_properties_on_a_large_lattice():
+    """Properties that hold at any size (used where no oracle can run):
+    (i) with unit masses, no potential and no damping, sum_i u_t(i) = sum(u_0) * (1 + t) exactly in
+        exact arithmetic (the Laplacian has zero column sums and u_{-1} = 0);
+    (ii) linearity: the response to a + b is the sum of the responses;
+    (iii) time reversal: swapping (u, u_prev) and stepping again retraces the trajectory."""
+    spec = tk.LatticeSpec(size=1024, dim=2)
+    k1, k2 = spec.bench_kick_node(), (17, 1000, "C")
+    kw = dict(c=1.0, dt=0.01, damping=0.0, probes=[k1, k2])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        ha = tk.run_wave_sim(spec, steps=40, initial_data={k1: 1.0}, **kw)
+        hb = tk.run_wave_sim(spec, steps=40, initial_data={k2: -2.0}, **kw)
+        hab = tk.run_wave_sim(spec, steps=40, initial_data={k1: 1.0, k2: -2.0}, **kw)
+    assert ha.final_state.sum() == pytest.approx(41.0, rel=1e-11)
+    assert hab.final_state.sum() == pytest.approx(-41.0, rel=1e-11)
+    scale = np.max(np.abs(hab.final_state))
+    assert np.max(np.abs(hab.final_state - (ha.final_state + hb.final_state))) < 1e-12 * scale
+    assert rel_inf(hab.probe_series, ha.probe_series + hb.probe_series) < 1e-12
+    # time reversal through the raw plan API
+    plan = tk.compile_lattice(spec)
+    try:
+        coeff = (1.0 * ha.dt) ** 2
+        plan.set_state_sparse([spec.index(k1)], [1.0])
+        plan.run(25, coeff, 0.0)
+        u, up = plan.get_state(want_prev=True)
+        plan.set_state(up, u)
+        plan.run(25, coeff, 0.0)
+        back, back_prev = plan.get_state(want_prev=True)
+    finally:
+        plan.close()
+    expect = np.zeros(spec.num_slots)
+    assert np.max(np.abs(back)) < 1e-9  # u_{-1} = 0
+    expect[spec.index(k1)] = 1.0
+    assert np.max(np.abs(back_prev - expect)) < 1e-9

@@ -1,0 +1,304 @@
+"""ctypes binding of ``include/tetrakis_b200.h`` -- the only way Python reaches the CUDA code.
+
+There is deliberately no fallback: if ``lib/libtetrakis_b200.so`` is missing or fails to load,
+:func:`lib` raises :class:`BackendUnavailable`; if no CUDA device is present every compute entry
+point returns ``TK_ERR_NO_DEVICE`` and :func:`check` raises :class:`NoDeviceError`.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_uint8, c_void_p
+
+import numpy as np
+
+from ._build import LIB_PATH
+
+TK_OK, TK_ERR_INVALID, TK_ERR_CUDA, TK_ERR_NOMEM, TK_ERR_NO_DEVICE = 0, 1, 2, 3, 4
+
+# every symbol declared in include/tetrakis_b200.h (tests check the .so exports all of them)
+ABI_SYMBOLS = (
+    "tk_abi_version", "tk_last_error", "tk_device_count", "tk_device_info",
+    "tk_graph_plan_create", "tk_lattice_plan_create",
+    "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
+    "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
+    "tk_plan_run", "tk_plan_launch_count", "tk_plan_destroy",
+    "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
+    "tk_lattice_step_end", "tk_dft_abs",
+)  # fmt: skip
+
+
+class BackendUnavailable(RuntimeError):
+    """The CUDA library is not built / not loadable.  There is no CPU path."""
+
+
+class NoDeviceError(RuntimeError):
+    """No CUDA device.  There is no CPU path."""
+
+
+class TkError(RuntimeError):
+    pass
+
+
+class LatticeDesc(ctypes.Structure):
+    _fields_ = [
+        ("size", c_int32), ("layers", c_int32), ("z_begin", c_int32), ("z_end", c_int32),
+        ("n_special", c_int64), ("special_index", c_void_p), ("special_flags", c_void_p),
+        ("special_inv_mass", c_void_p), ("special_potential", c_void_p),
+        ("n_corr", c_int64), ("corr_a", c_void_p), ("corr_b", c_void_p), ("corr_sign", c_void_p),
+    ]  # fmt: skip
+
+
+class RunArgs(ctypes.Structure):
+    _fields_ = [
+        ("steps", c_int64), ("coeff", c_double), ("damping", c_double),
+        ("n_probes", c_int64), ("probe_index", c_void_p), ("probe_out", c_void_p),
+        ("history_out", c_void_p), ("energy_out", c_void_p), ("elapsed_ms", c_void_p),
+        ("step_kernel_ms", c_void_p),
+    ]  # fmt: skip
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise BackendUnavailable(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  tetrakis-b200 has no CPU fallback."
+        )
+    try:
+        L = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:  # pragma: no cover - depends on the host
+        raise BackendUnavailable(f"cannot load {LIB_PATH}: {exc}") from exc
+    P = c_void_p
+    L.tk_abi_version.restype = c_int
+    L.tk_last_error.restype = c_char_p
+    L.tk_device_count.argtypes = [POINTER(c_int)]
+    L.tk_device_info.argtypes = [c_int, c_char_p, c_int, POINTER(c_int), POINTER(c_int),
+                                 POINTER(c_int), POINTER(c_int64)]  # fmt: skip
+    L.tk_graph_plan_create.argtypes = [c_int, c_int64, P, P, P, P, P, POINTER(P)]
+    L.tk_lattice_plan_create.argtypes = [c_int, POINTER(LatticeDesc), POINTER(P)]
+    L.tk_plan_set_stream.argtypes = [P, P]
+    L.tk_plan_num_nodes.argtypes = [P, POINTER(c_int64)]
+    L.tk_plan_max_degree.argtypes = [P, POINTER(c_int64)]
+    L.tk_plan_set_state_sparse.argtypes = [P, c_int64, P, P]
+    L.tk_plan_set_state.argtypes = [P, P, P]
+    L.tk_plan_get_state.argtypes = [P, P, P]
+    L.tk_plan_run.argtypes = [P, POINTER(RunArgs)]
+    L.tk_plan_launch_count.argtypes = [P, POINTER(c_int64)]
+    L.tk_plan_destroy.argtypes = [P]
+    L.tk_lattice_halo_ptrs.argtypes = [P, c_int32, POINTER(P), POINTER(P), POINTER(P), POINTER(P),
+                                       POINTER(c_int64)]  # fmt: skip
+    L.tk_lattice_step_begin.argtypes = [P, c_double, c_double]
+    L.tk_lattice_step_layers.argtypes = [P, c_int32, c_int32]
+    L.tk_lattice_step_end.argtypes = [P]
+    L.tk_dft_abs.argtypes = [c_int, P, c_int64, c_int64, P, P]
+    for name in ABI_SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("tk_last_error",):
+            fn.restype = c_int
+    if L.tk_abi_version() != 1:
+        raise BackendUnavailable(f"ABI version mismatch: library reports {L.tk_abi_version()}")
+    _LIB = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc == TK_OK:
+        return
+    msg = lib().tk_last_error().decode("utf-8", "replace")
+    if rc == TK_ERR_NO_DEVICE:
+        raise NoDeviceError(msg)
+    if rc == TK_ERR_INVALID:
+        raise ValueError(msg)
+    if rc == TK_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise TkError(msg)
+
+
+def device_count() -> int:
+    n = c_int(0)
+    check(lib().tk_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def device_info(device: int = 0) -> dict:
+    name = ctypes.create_string_buffer(256)
+    sm, maj, mnr, mem = c_int(0), c_int(0), c_int(0), c_int64(0)
+    check(lib().tk_device_info(device, name, 256, ctypes.byref(sm), ctypes.byref(maj),
+                               ctypes.byref(mnr), ctypes.byref(mem)))  # fmt: skip
+    return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value),
+            "total_mem": mem.value}  # fmt: skip
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class Plan:
+    """Owner of one ``tk_plan`` (device buffers freed on :meth:`close` / garbage collection)."""
+
+    def __init__(self, handle, kind: str):
+        self._h = handle
+        self.kind = kind
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def graph(cls, rowptr, colidx, degree, inv_mass, potential, device: int = 0) -> "Plan":
+        rowptr = _arr(rowptr, np.int64)
+        colidx = _arr(colidx, np.int32)
+        degree = _arr(degree, np.float64)
+        inv_mass = _arr(inv_mass, np.float64)
+        potential = _arr(potential, np.float64)
+        n = len(rowptr) - 1
+        if not (len(degree) == len(inv_mass) == len(potential) == n):
+            raise ValueError("graph arrays disagree on the node count")
+        h = c_void_p()
+        check(lib().tk_graph_plan_create(device, n, _p(rowptr), _p(colidx), _p(degree),
+                                         _p(inv_mass), _p(potential), ctypes.byref(h)))  # fmt: skip
+        return cls(h, "graph")
+
+    @classmethod
+    def lattice(cls, size, layers, *, z_begin=0, z_end=None, special_index=None,
+                special_flags=None, special_inv_mass=None, special_potential=None, corr=None,
+                device: int = 0) -> "Plan":  # fmt: skip
+        si = _arr(special_index if special_index is not None else [], np.int64)
+        sf = _arr(special_flags if special_flags is not None else [], np.uint8)
+        sm = _arr(special_inv_mass, np.float64)
+        sv = _arr(special_potential, np.float64)
+        if len(si) != len(sf):
+            raise ValueError("special_index / special_flags length mismatch")
+        corr = corr or []
+        ca = _arr([c[0] for c in corr], np.int64)
+        cb = _arr([c[1] for c in corr], np.int64)
+        cs = _arr([c[2] for c in corr], np.float64)
+        d = LatticeDesc(int(size), int(layers), int(z_begin),
+                        int(layers if z_end is None else z_end), len(si), _p(si), _p(sf), _p(sm),
+                        _p(sv), len(ca), _p(ca), _p(cb), _p(cs))  # fmt: skip
+        h = c_void_p()
+        check(lib().tk_lattice_plan_create(device, ctypes.byref(d), ctypes.byref(h)))
+        return cls(h, "lattice")
+
+    # -- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib().tk_plan_destroy(self._h)
+        self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- queries ------------------------------------------------------------------------------
+    @property
+    def num_nodes(self) -> int:
+        n = c_int64(0)
+        check(lib().tk_plan_num_nodes(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def max_degree(self) -> int:
+        n = c_int64(0)
+        check(lib().tk_plan_max_degree(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def launches(self) -> int:
+        n = c_int64(0)
+        check(lib().tk_plan_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def set_stream(self, cuda_stream: int):
+        check(lib().tk_plan_set_stream(self._h, c_void_p(cuda_stream)))
+
+    # -- state --------------------------------------------------------------------------------
+    def set_state_sparse(self, index, value):
+        index = _arr(index, np.int64)
+        value = _arr(value, np.float64)
+        check(lib().tk_plan_set_state_sparse(self._h, len(index), _p(index), _p(value)))
+
+    def set_state(self, u, u_prev=None):
+        u = _arr(u, np.float64).reshape(-1)
+        up = None if u_prev is None else _arr(u_prev, np.float64).reshape(-1)
+        n = self.num_nodes
+        if u.size != n or (up is not None and up.size != n):
+            raise ValueError(f"state arrays must have {n} entries")
+        check(lib().tk_plan_set_state(self._h, _p(u), _p(up)))
+
+    def get_state(self, want_prev: bool = False):
+        n = self.num_nodes
+        u = np.empty(n, dtype=np.float64)
+        up = np.empty(n, dtype=np.float64) if want_prev else None
+        check(lib().tk_plan_get_state(self._h, _p(u), _p(up)))
+        return (u, up) if want_prev else u
+
+    # -- stepping -----------------------------------------------------------------------------
+    def run(self, steps, coeff, damping, *, probes=None, history=False, timed=False,
+            probe_out=None, history_out=None):  # fmt: skip
+        """``steps`` leapfrog updates.  Returns dict(probes, history, elapsed_ms)."""
+        steps = int(steps)
+        pidx = _arr(probes if probes is not None else [], np.int64)
+        pout = None
+        if len(pidx):
+            pout = probe_out if probe_out is not None else np.empty((steps + 1, len(pidx)))
+        hout = None
+        if history:
+            hout = (history_out if history_out is not None
+                    else np.empty((steps + 1, self.num_nodes), dtype=np.float64))  # fmt: skip
+        ms, kms = c_double(0.0), c_double(0.0)
+        a = RunArgs(steps, float(coeff), float(damping), len(pidx), _p(pidx), _p(pout), _p(hout),
+                    None, ctypes.cast(ctypes.byref(ms), c_void_p) if timed else None,
+                    ctypes.cast(ctypes.byref(kms), c_void_p) if timed else None)  # fmt: skip
+        check(lib().tk_plan_run(self._h, ctypes.byref(a)))
+        return {"probes": pout, "history": hout, "elapsed_ms": ms.value if timed else None,
+                "step_kernel_ms": kms.value if timed else None}
+
+    # -- slab phases (multi-GPU) --------------------------------------------------------------
+    def halo_ptrs(self, next_state: bool = False):
+        sl, sh, rl, rh = c_void_p(), c_void_p(), c_void_p(), c_void_p()
+        nb = c_int64(0)
+        check(lib().tk_lattice_halo_ptrs(self._h, int(next_state), ctypes.byref(sl), ctypes.byref(sh),
+                                         ctypes.byref(rl), ctypes.byref(rh), ctypes.byref(nb)))  # fmt: skip
+        return {"send_lo": sl.value, "send_hi": sh.value, "recv_lo": rl.value,
+                "recv_hi": rh.value, "plane_bytes": nb.value}  # fmt: skip
+
+    def step_begin(self, coeff, damping):
+        check(lib().tk_lattice_step_begin(self._h, float(coeff), float(damping)))
+
+    def step_layers(self, zl_begin, zl_end):
+        check(lib().tk_lattice_step_layers(self._h, int(zl_begin), int(zl_end)))
+
+    def step_end(self):
+        check(lib().tk_lattice_step_end(self._h))
+
+
+def dft_abs(series, device: int = 0):
+    """|DFT| and argmax of one (n,) or many (batch, n) real series on the device."""
+    x = np.ascontiguousarray(series, dtype=np.float64)
+    single = x.ndim == 1
+    x2 = x.reshape(1, -1) if single else x
+    spec = np.empty_like(x2)
+    arg = np.empty(x2.shape[0], dtype=np.int64)
+    check(lib().tk_dft_abs(device, _p(x2), x2.shape[0], x2.shape[1], _p(spec), _p(arg)))
+    return (spec[0], int(arg[0])) if single else (spec, arg)
+
+
+__all__ = ["Plan", "lib", "check", "device_count", "device_info", "dft_abs", "ABI_SYMBOLS",
+           "BackendUnavailable", "NoDeviceError", "TkError", "c_uint8"]  # fmt: skip

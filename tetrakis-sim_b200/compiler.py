@@ -1,0 +1,158 @@
+"""One-time graph-to-device compiler.
+
+Turns what ``run_wave_sim`` receives into a device plan:
+
+* any ``networkx`` graph  -> :func:`compile_graph`: node list, adjacency-ordered CSR, degrees,
+  inv_mass / potential exactly as the reference precomputes them
+  (``tetrakis_sim/physics.py:56-64, 93-102``), handed to ``tk_graph_plan_create`` (sliced ELL on
+  the device; bit-identical results).
+* a :class:`LatticeSpec`  -> :func:`compile_lattice`: the sparse defect description handed to
+  ``tk_lattice_plan_create`` (structured clique-sum kernel; lattices of any size).
+* a ``networkx`` graph that *is* a tetrakis lattice can also be routed to the structured kernel
+  (:func:`structured_from_graph`): the (alive, part, mass, potential) model is read off the
+  graph and every edge on which graph and model differ becomes an explicit correction, so the
+  result is the same operator.  Used for cross-checking the two kernels.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import Plan
+from .lattice import FLAG_ALIVE, FLAG_PART, QUADRANTS, LatticeSpec
+
+
+@dataclass
+class CompiledGraph:
+    plan: Plan
+    nodes: list  # list(G.nodes)
+    index: dict  # node -> row
+    max_degree: int
+    state_index: np.ndarray | None = None  # row -> device state index (lattice route) or None
+
+
+def graph_arrays(G):
+    """(nodes, index, rowptr, colidx, degree, inv_mass, potential) -- physics.py:56-64, 93-102."""
+    nodes = list(G.nodes)
+    index = {n: i for i, n in enumerate(nodes)}
+    n = len(nodes)
+    adj = G.adj
+    counts = np.fromiter((len(adj[v]) for v in nodes), dtype=np.int64, count=n)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=rowptr[1:])
+    colidx = np.fromiter(
+        (index[m] for v in nodes for m in adj[v]), dtype=np.int32, count=int(rowptr[-1])
+    )
+    deg_map = dict(G.degree(nodes))
+    degree = np.fromiter((deg_map[v] for v in nodes), dtype=np.float64, count=n)
+    inv_mass = np.ones(n, dtype=np.float64)
+    potential = np.zeros(n, dtype=np.float64)
+    for v, attrs in G.nodes(data=True):
+        if attrs:
+            if "mass" in attrs:
+                m = float(attrs["mass"])
+                if m <= 0.0:
+                    m = 1.0
+                inv_mass[index[v]] = 1.0 / m
+            if "potential" in attrs:
+                potential[index[v]] = float(attrs["potential"])
+    return nodes, index, rowptr, colidx, degree, inv_mass, potential
+
+
+def compile_graph(G, device: int = 0) -> CompiledGraph:
+    nodes, index, rowptr, colidx, degree, inv_mass, potential = graph_arrays(G)
+    plan = Plan.graph(rowptr, colidx, degree, inv_mass, potential, device=device)
+    max_degree = int(degree.max()) if len(nodes) else 0
+    return CompiledGraph(plan, nodes, index, max_degree)
+
+
+def compile_lattice(spec: LatticeSpec, device: int = 0, z_begin: int = 0, z_end: int | None = None) -> Plan:
+    idx, flags, im, pot = spec.specials()
+    return Plan.lattice(
+        spec.size, spec.layers, z_begin=z_begin, z_end=z_end, special_index=idx,
+        special_flags=flags, special_inv_mass=im, special_potential=pot,
+        corr=spec.corrections(), device=device,
+    )  # fmt: skip
+
+
+def detect_lattice_shape(G):
+    """(dim, size, layers) if every node looks like a tetrakis node tuple, else None."""
+    dim = None
+    rmax = cmax = zmax = -1
+    for n in G.nodes:
+        if not isinstance(n, tuple) or len(n) not in (3, 4) or n[-1] not in QUADRANTS:
+            return None
+        if dim is None:
+            dim = 2 if len(n) == 3 else 3
+        elif (len(n) == 3) != (dim == 2):
+            return None
+        if not all(isinstance(x, (int, np.integer)) and x >= 0 for x in n[:-1]):
+            return None
+        rmax = max(rmax, n[0])
+        cmax = max(cmax, n[1])
+        if dim == 3:
+            zmax = max(zmax, n[2])
+    if dim is None:
+        return None
+    return dim, max(rmax, cmax) + 1, (zmax + 1 if dim == 3 else 1)
+
+
+def structured_from_graph(G, shape=None, device: int = 0) -> CompiledGraph:
+    """Route a tetrakis-shaped ``networkx`` graph to the structured kernel.
+
+    O(E) host work (it enumerates the model's edges to diff them against G), so this is for
+    graphs networkx can hold anyway."""
+    shape = shape or detect_lattice_shape(G)
+    if shape is None:
+        raise ValueError("graph nodes are not tetrakis (r, c[, z], q) tuples")
+    dim, S, L = shape
+    spec = LatticeSpec(size=S, dim=dim, layers=L)
+    nodes = list(G.nodes)
+    index = {n: i for i, n in enumerate(nodes)}
+    gidx = np.fromiter((spec.index(n) for n in nodes), dtype=np.int64, count=len(nodes))
+    deg_map = dict(G.degree(nodes))
+    alive = np.zeros(spec.num_slots, dtype=bool)
+    part = np.zeros(spec.num_slots, dtype=bool)
+    inv_mass = np.ones(spec.num_slots)
+    potential = np.zeros(spec.num_slots)
+    for n, gi in zip(nodes, gidx):
+        alive[gi] = True
+        part[gi] = deg_map[n] > 0
+        a = G.nodes[n]
+        if a:
+            m = float(a.get("mass", 1.0))
+            inv_mass[gi] = 1.0 / (m if m > 0.0 else 1.0)
+            potential[gi] = float(a.get("potential", 0.0))
+    sp = np.flatnonzero(~(alive & part) | (inv_mass != 1.0) | (potential != 0.0))
+    flags = (alive[sp] * FLAG_ALIVE + part[sp] * FLAG_PART).astype(np.uint8)
+    # model edges vs graph edges
+    P4 = part.reshape(L, S, S, 4)
+    model = set()
+    plane = S * S * 4
+    for z, r, c, q in zip(*np.nonzero(P4)):
+        a = ((z * S + r) * S + c) * 4 + q
+        for q2 in range(q + 1, 4):
+            if P4[z, r, c, q2]:
+                model.add((a, a - q + q2))
+        for c2 in np.flatnonzero(P4[z, r, c + 1 :, q]):
+            model.add((a, a + (int(c2) + 1) * 4))
+        for r2 in np.flatnonzero(P4[z, r + 1 :, c, q]):
+            model.add((a, a + (int(r2) + 1) * S * 4))
+        if z + 1 < L and P4[z + 1, r, c, q]:
+            model.add((a, a + plane))
+    graph = set()
+    for a, b in G.edges:
+        ia, ib = int(gidx[index[a]]), int(gidx[index[b]])
+        graph.add((min(ia, ib), max(ia, ib)))
+    corr = []
+    for a, b in sorted(model - graph):
+        corr += [(int(a), int(b), -1.0), (int(b), int(a), -1.0)]
+    for a, b in sorted(graph - model):
+        corr += [(a, b, 1.0), (b, a, 1.0)]
+    plan = Plan.lattice(S, L, special_index=sp, special_flags=flags,
+                        special_inv_mass=inv_mass[sp], special_potential=potential[sp], corr=corr,
+                        device=device)  # fmt: skip
+    max_degree = max(deg_map.values(), default=0)
+    return CompiledGraph(plan, nodes, index, int(max_degree), state_index=gidx)

@@ -1,0 +1,349 @@
+// Structured ("clique-sum") leapfrog step for tetrakis lattices -- the hot kernel.
+//
+// Replaces the triple Python loop of reference tetrakis_sim/physics.py:106-129 on graphs built by
+// lattice.py:15-76 (+ defects.py).  Every row and column of same-quadrant nodes is a clique
+// (lattice.py:37-44, 61-66), so the neighbour sum collapses to
+//     (CellSum - u) + (RowSum[z,r,q] - u) + (ColSum[z,c,q] - u) + u(z-1) + u(z+1)
+// and one fused, memory-bound pass per step suffices:
+//     read u_t, read u_{t-1}, write u_{t+1} in place of u_{t-1}     = 24 B / node-update (fp64)
+// while producing the partial row / column sums of u_{t+1} for the next step.
+//
+// Layout: state[plane][r][c][q], q fastest (32 B per cell); plane = local layer + halo.
+// Work decomposition: a warp owns a segment of 32*CPL consecutive cells of one (layer, row) --
+// CPL*1 KB contiguous per array -- and marches down `rchunk` rows, so column sums accumulate in
+// registers and row sums need one transposing warp reduction per row.  A CTA is 8 warps: WC
+// adjacent segments x WZ = 8/WC consecutive layers (the z+-1 neighbours of the interior warps are
+// the same lines their sibling warps stream in, so they hit L1/L2 instead of HBM).
+// Defects are sparse: a per-(layer,row,64-cell) table says "plain" (-1) or points at a detail
+// record (participation bits, mass/potential, edge corrections) used by a slower path.
+#pragma once
+#include "common.cuh"
+
+namespace tk {
+
+constexpr int kTabSeg = 64;  // cells per defect-table segment (independent of CPL)
+
+struct LatDev {
+    int S;          // cells per side
+    int Lloc;       // owned layers
+    int halo;       // 1 if halo planes exist (3-D), 0 for a 2-D sheet
+    int ntab;       // table segments per row = ceil(S / 64)
+    int has_below;  // a layer exists below local layer 0 (z_begin > 0)
+    int has_above;  // a layer exists above local layer Lloc-1
+    const int *seg_flag;            // [Lloc][S][ntab]   -1 plain, else detail index
+    const unsigned short *det_flags;  // [ndet][64] bits 0-3 part(q) 4-7 alive(q) 8-11 part(z-1,q) 12-15 part(z+1,q)
+    const int *det_attr;            // [ndet] -1 or row of attr_im / attr_v
+    const int2 *det_corr;           // [ndet] [begin, end) into corr_*
+    const double *attr_im;          // [nattr][256] inv_mass per node of the segment
+    const double *attr_v;           // [nattr][256] potential
+    const long long *corr_a;        // padded-local node index that receives the correction
+    const long long *corr_b;        // padded-local node index whose u is added
+    const double *corr_sign;
+    const double *rowinfo;  // [Lloc][S][8]: 0-3 RowSum(q) of the current state, 4-7 row participation count
+    const double *colinfo;  // [Lloc][S][8]: same for columns
+};
+
+__device__ __forceinline__ unsigned plain_flags(const LatDev &P, int zl)
+{
+    unsigned f = 0xFFu;
+    if (zl > 0 || P.has_below) f |= 0xF00u;
+    if (zl < P.Lloc - 1 || P.has_above) f |= 0xF000u;
+    return f;
+}
+
+// Inputs / outputs of one cell (4 quadrant nodes) on the defect-aware path.  Passed by reference
+// to an out-of-line function so that the rarely taken path costs the streaming path no registers.
+struct CellIO {
+    double uq[4], upq[4], zm[4], zp[4], RS[4], RC[4], CS[4], CC[4];
+    double un[4], pun[4];
+};
+
+//   io.un[q] <- u_{t+1};  io.pun[q] <- participation-masked u_{t+1} (what row/col sums accumulate)
+__device__ __noinline__ void cell_update_detail(const LatDev &P, const double *__restrict__ ustate,
+                                                int det, int cell_in_tab, long long node0,
+                                                unsigned f, double coeff, double damping, CellIO &io)
+{
+    double cell = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if ((f >> q) & 1u) cell += io.uq[q];
+    const double ccnt = (double)__popc(f & 0xFu);
+    int attr = -1;
+    int2 cr = make_int2(0, 0);
+    if (det >= 0) {
+        attr = P.det_attr[det];
+        cr = P.det_corr[det];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const bool part = (f >> q) & 1u, alive = (f >> (4 + q)) & 1u;
+        const double uq = io.uq[q], upq = io.upq[q];
+        double lap = 0.0;
+        if (part) {
+            const bool pm = (f >> (8 + q)) & 1u, pp = (f >> (12 + q)) & 1u;
+            double nsum = (cell - uq) + (io.RS[q] - uq) + (io.CS[q] - uq);
+            double deg = (ccnt - 1.0) + (io.RC[q] - 1.0) + (io.CC[q] - 1.0);
+            if (pm) { nsum += io.zm[q]; deg += 1.0; }
+            if (pp) { nsum += io.zp[q]; deg += 1.0; }
+            lap = nsum - deg * uq;
+        }
+        for (int k = cr.x; k < cr.y; ++k)
+            if (P.corr_a[k] == node0 + q) lap += P.corr_sign[k] * (ustate[P.corr_b[k]] - uq);
+        double im = 1.0, v = 0.0;
+        if (attr >= 0) {
+            im = P.attr_im[(size_t)attr * 256 + cell_in_tab * 4 + q];
+            v = P.attr_v[(size_t)attr * 256 + cell_in_tab * 4 + q];
+        }
+        const double r = 2.0 * uq - upq + (coeff * im) * lap - (coeff * v) * uq - damping * (uq - upq);
+        io.un[q] = alive ? r : 0.0;
+        io.pun[q] = part ? io.un[q] : 0.0;
+    }
+}
+
+// MODE 0: leapfrog step.  MODE 1: sums only (row/col sums of the current state, no update).
+template <int CPL, int WC, bool K3D, int MODE>
+__global__ void __launch_bounds__(256)
+lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
+                double *__restrict__ w, double *__restrict__ prow, double *__restrict__ pcol,
+                double coeff, double damping, int zl_begin, int zl_end, int rchunk, int nchunk,
+                int nsegk, int nct, int nzg)
+{
+    constexpr int WZ = 8 / WC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b = blockIdx.x;
+    const int zg = b % nzg;
+    b /= nzg;
+    const int ct = b % nct;
+    const int ch = b / nct;
+    const int zl = zl_begin + zg * WZ + warp / WC;
+    const int segk = ct * WC + warp % WC;
+    if (zl >= zl_end || segk >= nsegk) return;  // whole warp leaves; no block-level sync below
+
+    const int S = P.S;
+    const int c0 = (segk * 32 + lane) * CPL;
+    bool valid[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) valid[j] = (c0 + j) < S;
+    const size_t plane = (size_t)S * S * 4;
+    const size_t zbase = (size_t)(zl + P.halo) * plane;
+    const unsigned fplain = plain_flags(P, zl);
+    const bool zm_on = K3D && (fplain & 0x100u), zp_on = K3D && (fplain & 0x1000u);
+    const double degbase = 4.0 + (zm_on ? 1.0 : 0.0) + (zp_on ? 1.0 : 0.0);
+
+    // column context: constant while marching down the rows
+    double CS[CPL][4], CC[CPL][4], cacc[CPL][4];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            CS[j][q] = 0.0;
+            CC[j][q] = 0.0;
+            cacc[j][q] = 0.0;
+        }
+    if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j)
+            if (valid[j]) {
+                const double2 *ci = reinterpret_cast<const double2 *>(
+                    P.colinfo + ((size_t)zl * S + (c0 + j)) * 8);
+                const double2 a = ci[0], bb = ci[1], c = ci[2], d = ci[3];
+                CS[j][0] = a.x; CS[j][1] = a.y; CS[j][2] = bb.x; CS[j][3] = bb.y;
+                CC[j][0] = c.x; CC[j][1] = c.y; CC[j][2] = d.x; CC[j][3] = d.y;
+            }
+    }
+
+    const int r_begin = ch * rchunk;
+    const int r_end = min(S, r_begin + rchunk);
+    const int tab0 = c0 / kTabSeg;  // all CPL cells of a lane share a table segment (CPL | 64)
+
+    for (int r = r_begin; r < r_end; ++r) {
+        const size_t rowoff = zbase + ((size_t)r * S + c0) * 4;
+        double uq[CPL][4], upq[CPL][4], zm[CPL][4], zp[CPL][4];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            if (valid[j]) {
+                const double2 *pu = reinterpret_cast<const double2 *>(u + rowoff + j * 4);
+                const double2 a = pu[0], bb = pu[1];
+                uq[j][0] = a.x; uq[j][1] = a.y; uq[j][2] = bb.x; uq[j][3] = bb.y;
+                if (MODE == 0) {
+                    const double2 *pw = reinterpret_cast<const double2 *>(w + rowoff + j * 4);
+                    const double2 c = __ldcs(pw), d = __ldcs(pw + 1);
+                    upq[j][0] = c.x; upq[j][1] = c.y; upq[j][2] = d.x; upq[j][3] = d.y;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { uq[j][q] = 0.0; upq[j][q] = 0.0; }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { zm[j][q] = 0.0; zp[j][q] = 0.0; }
+            if (MODE == 0 && K3D && valid[j]) {
+                if (zm_on) {
+                    const double2 *pz = reinterpret_cast<const double2 *>(u + rowoff - plane + j * 4);
+                    const double2 a = pz[0], bb = pz[1];
+                    zm[j][0] = a.x; zm[j][1] = a.y; zm[j][2] = bb.x; zm[j][3] = bb.y;
+                }
+                if (zp_on) {
+                    const double2 *pz = reinterpret_cast<const double2 *>(u + rowoff + plane + j * 4);
+                    const double2 a = pz[0], bb = pz[1];
+                    zp[j][0] = a.x; zp[j][1] = a.y; zp[j][2] = bb.x; zp[j][3] = bb.y;
+                }
+            }
+        }
+        int det = -1;
+        if (c0 < S) det = P.seg_flag[((size_t)zl * S + r) * P.ntab + tab0];
+        const bool all_plain = __all_sync(0xffffffffu, det < 0);
+
+        double RS[4] = {0, 0, 0, 0}, RC[4] = {0, 0, 0, 0};
+        if (MODE == 0) {
+            const double2 *ri = reinterpret_cast<const double2 *>(P.rowinfo + ((size_t)zl * S + r) * 8);
+            const double2 a = ri[0], bb = ri[1], c = ri[2], d = ri[3];
+            RS[0] = a.x; RS[1] = a.y; RS[2] = bb.x; RS[3] = bb.y;
+            RC[0] = c.x; RC[1] = c.y; RC[2] = d.x; RC[3] = d.y;
+        }
+
+        double rsum[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            double un[4], pun[4];
+            if (MODE == 1) {
+                unsigned f = fplain;
+                if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + ((c0 + j) & (kTabSeg - 1))];
+                if (!valid[j]) f = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pun[q] = ((f >> q) & 1u) ? uq[j][q] : 0.0;
+            } else if (all_plain) {
+                const double cell = (uq[j][0] + uq[j][1]) + (uq[j][2] + uq[j][3]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double nb = (cell + RS[q]) + (CS[j][q] + (zm[j][q] + zp[j][q]));
+                    const double dg = (RC[q] + degbase) + CC[j][q];
+                    const double lap = nb - dg * uq[j][q];
+                    un[q] = 2.0 * uq[j][q] - upq[j][q] + coeff * lap -
+                            damping * (uq[j][q] - upq[j][q]);
+                    pun[q] = valid[j] ? un[q] : 0.0;
+                }
+            } else {
+                unsigned f = fplain;
+                if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + ((c0 + j) & (kTabSeg - 1))];
+                if (!valid[j]) f = 0;
+                CellIO io;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    io.uq[q] = uq[j][q]; io.upq[q] = upq[j][q]; io.zm[q] = zm[j][q]; io.zp[q] = zp[j][q];
+                    io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[j][q]; io.CC[q] = CC[j][q];
+                }
+                cell_update_detail(P, u, det, (c0 + j) & (kTabSeg - 1), (long long)(rowoff + j * 4), f,
+                                   coeff, damping, io);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { un[q] = io.un[q]; pun[q] = io.pun[q]; }
+            }
+            if (MODE == 0 && valid[j]) {
+                double2 *pw = reinterpret_cast<double2 *>(w + rowoff + j * 4);
+                __stcs(pw, make_double2(un[0], un[1]));
+                __stcs(pw + 1, make_double2(un[2], un[3]));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                cacc[j][q] += pun[q];
+                rsum[q] += pun[q];
+            }
+        }
+        warp_sum4_store(rsum, lane, prow + (((size_t)zl * S + r) * nsegk + segk) * 4);
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+        if (valid[j]) {
+            double2 *pc = reinterpret_cast<double2 *>(pcol + (((size_t)zl * nchunk + ch) * S + (c0 + j)) * 4);
+            pc[0] = make_double2(cacc[j][0], cacc[j][1]);
+            pc[1] = make_double2(cacc[j][2], cacc[j][3]);
+        }
+}
+
+// Deterministic finalise: fixed-order sums of the partials written by lat_step_kernel, plus the
+// probe gather (reference physics.py:162 reads one node per recorded state).
+//   threads [0, Lloc*S*4)            -> RowSum[zl][r][q]
+//   threads [Lloc*S*4, 2*Lloc*S*4)   -> ColSum[zl][c][q]
+//   first n_probes threads of block 0 also gather probes from the NEW state `state`.
+__global__ void __launch_bounds__(256)
+lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, const double *__restrict__ prow,
+                    const double *__restrict__ pcol, double *__restrict__ rowinfo,
+                    double *__restrict__ colinfo, const double *__restrict__ state,
+                    const long long *__restrict__ probe_idx, int n_probes,
+                    double *__restrict__ probe_row)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nline = (long long)Lloc * S * 4;
+    if (t < n_probes) probe_row[t] = state[probe_idx[t]];
+    if (t < nline) {
+        const long long line = t >> 2;
+        const int q = (int)(t & 3);
+        const double *p = prow + (size_t)line * nsegk * 4 + q;
+        double acc = 0.0;
+        for (int s = 0; s < nsegk; ++s) acc += p[(size_t)s * 4];
+        rowinfo[line * 8 + q] = acc;
+    } else if (t < 2 * nline) {
+        const long long tt = t - nline;
+        const long long line = tt >> 2;  // zl*S + c
+        const int q = (int)(tt & 3);
+        const long long zl = line / S, c = line % S;
+        const double *p = pcol + ((size_t)zl * nchunk * S + c) * 4 + q;
+        double acc = 0.0;
+        for (int k = 0; k < nchunk; ++k) acc += p[(size_t)k * S * 4];
+        colinfo[line * 8 + q] = acc;
+    }
+}
+
+// max over existing nodes of the graph degree (reference physics.py:60-64), from the tables.
+__global__ void __launch_bounds__(256)
+lat_maxdeg_kernel(const __grid_constant__ LatDev P, int *__restrict__ out)
+{
+    const long long ncell = (long long)P.Lloc * P.S * P.S;
+    int best = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % P.S);
+        const long long zr = i / P.S;
+        const int r = (int)(zr % P.S), zl = (int)(zr / P.S);
+        const int det = P.seg_flag[(size_t)zr * P.ntab + c / kTabSeg];
+        unsigned f = plain_flags(P, zl);
+        int2 cr = make_int2(0, 0);
+        if (det >= 0) {
+            f = P.det_flags[(size_t)det * kTabSeg + (c & (kTabSeg - 1))];
+            cr = P.det_corr[det];
+        }
+        const int ccnt = __popc(f & 0xFu);
+        const long long node0 = (((long long)(zl + P.halo) * P.S + r) * P.S + c) * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!((f >> (4 + q)) & 1u)) continue;
+            int deg = 0;
+            if ((f >> q) & 1u) {
+                deg = (ccnt - 1) + ((int)P.rowinfo[((size_t)zl * P.S + r) * 8 + 4 + q] - 1) +
+                      ((int)P.colinfo[((size_t)zl * P.S + c) * 8 + 4 + q] - 1) +
+                      (int)((f >> (8 + q)) & 1u) + (int)((f >> (12 + q)) & 1u);
+            }
+            for (int k = cr.x; k < cr.y; ++k)
+                if (P.corr_a[k] == node0 + q) deg += (int)P.corr_sign[k];
+            best = max(best, deg);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(out, best);
+}
+
+__global__ void scatter_kernel(double *__restrict__ dst, const long long *__restrict__ idx,
+                               const double *__restrict__ val, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = val[i];
+}
+
+__global__ void gather_kernel(const double *__restrict__ src, const long long *__restrict__ idx,
+                              double *__restrict__ out, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+
+}  // namespace tk

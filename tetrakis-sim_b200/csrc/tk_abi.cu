@@ -1,0 +1,915 @@
+// C ABI of the tetrakis-b200 hot path (see include/tetrakis_b200.h for the contract).
+// Host side: plan construction (graph -> sliced ELL; lattice descriptor -> defect tables),
+// the stepping loops and all CUDA resource management.  No CPU compute fallback anywhere.
+#include "../../include/tetrakis_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels_graph.cuh"
+#include "kernels_lattice.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define TK_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(e_ == cudaErrorMemoryAllocation ? TK_ERR_NOMEM : TK_ERR_CUDA,          \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define TK_REQUIRE(cond, ...)                                    \
+    do {                                                         \
+        if (!(cond)) return fail(TK_ERR_INVALID, __VA_ARGS__);   \
+    } while (0)
+
+int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TK_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); tetrakis-b200 has no CPU path",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(TK_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    TK_CUDA(cudaSetDevice(device));
+    return TK_OK;
+}
+
+template <typename T>
+int dev_alloc(T **p, size_t count)
+{
+    *p = nullptr;
+    if (count == 0) count = 1;
+    TK_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+    return TK_OK;
+}
+
+template <typename T>
+int dev_upload(T **p, const std::vector<T> &v)
+{
+    int rc = dev_alloc(p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) TK_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return TK_OK;
+}
+
+enum PlanKind { kGraph = 1, kLattice = 2 };
+
+constexpr size_t kHistoryChunkBytes = (size_t)1 << 30;
+
+}  // namespace
+
+struct tk_plan {
+    int kind = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    long long n = 0;          // local nodes visible through the ABI
+    long long alloc = 0;      // doubles per state buffer
+    long long state_off = 0;  // ABI index 0 lives at this offset in a state buffer
+    double *buf[2] = {nullptr, nullptr};
+    int cur = 0;  // buf[cur] = u_t, buf[cur^1] = u_{t-1} (overwritten by u_{t+1})
+    long long launches = 0;
+    long long max_degree = -1;
+    std::vector<void *> owned;  // device allocations to free
+
+    // probes
+    long long *probe_idx = nullptr;  // device, buffer-relative indices
+    int n_probes = 0;
+    double *probe_series = nullptr;  // device, rows x n_probes
+    long long probe_rows_cap = 0;
+    long long probe_row = 0;
+
+    // graph
+    long long *slice_off = nullptr;
+    int *ell_idx = nullptr;
+    double *deg = nullptr, *inv_mass = nullptr, *potential = nullptr;
+
+    // lattice
+    tk::LatDev lat{};
+    double *rowinfo = nullptr, *colinfo = nullptr, *prow = nullptr, *pcol = nullptr;
+    int cpl = 2, wc = 8, rchunk = 64, nchunk = 1, nsegk = 1;
+    int layers_global = 1, z_begin = 0;
+    double coeff = 0.0, damping = 0.0;
+    std::vector<long long> dead_local;  // ABI-local indices of removed nodes (for dense set_state)
+};
+
+namespace {
+
+int plan_common_init(tk_plan *p, int device)
+{
+    p->device = device;
+    TK_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    p->own_stream = true;
+    cudaDeviceProp prop;
+    TK_CUDA(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+    return TK_OK;
+}
+
+template <typename T>
+int plan_upload(tk_plan *p, T **dst, const std::vector<T> &v)
+{
+    int rc = dev_upload(dst, v);
+    if (rc == TK_OK) p->owned.push_back((void *)*dst);
+    return rc;
+}
+
+template <typename T>
+int plan_alloc(tk_plan *p, T **dst, size_t count, bool zero)
+{
+    int rc = dev_alloc(dst, count);
+    if (rc) return rc;
+    p->owned.push_back((void *)*dst);
+    if (zero) TK_CUDA(cudaMemset(*dst, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    return TK_OK;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// ------------------------------------------------------------------ lattice launches
+template <int CPL, int WC, bool K3D, int MODE>
+int launch_lat(tk_plan *p, int zl_begin, int zl_end)
+{
+    constexpr int WZ = 8 / WC;
+    const int nsegk = p->nsegk;
+    const int nct = (nsegk + WC - 1) / WC;
+    const int nzg = (zl_end - zl_begin + WZ - 1) / WZ;
+    const long long grid = (long long)p->nchunk * nct * nzg;
+    if (grid <= 0) return TK_OK;
+    if (grid > 0x7fffffffLL) return fail(TK_ERR_INVALID, "lattice grid too large");
+    tk::lat_step_kernel<CPL, WC, K3D, MODE><<<(unsigned)grid, 256, 0, p->stream>>>(
+        p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
+        zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg);
+    p->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TK_OK;
+}
+
+template <int MODE>
+int launch_lat_dispatch(tk_plan *p, int zl_begin, int zl_end)
+{
+    const bool k3d = p->lat.halo != 0;
+#define TK_CASE(CPL, WC)                                                         \
+    if (p->cpl == CPL && p->wc == WC)                                            \
+        return k3d ? launch_lat<CPL, WC, true, MODE>(p, zl_begin, zl_end)        \
+                   : launch_lat<CPL, WC, false, MODE>(p, zl_begin, zl_end);
+    TK_CASE(1, 8) TK_CASE(1, 2) TK_CASE(1, 1)
+    TK_CASE(2, 8) TK_CASE(2, 2) TK_CASE(2, 1)
+    TK_CASE(4, 8) TK_CASE(4, 1)
+#undef TK_CASE
+    return fail(TK_ERR_INVALID, "unsupported lattice kernel variant cpl=%d wc=%d", p->cpl, p->wc);
+}
+
+int lat_finalise(tk_plan *p, const double *state, double *probe_row)
+{
+    const long long threads = 2LL * p->lat.Lloc * p->lat.S * 4;
+    const unsigned grid = (unsigned)((std::max<long long>(threads, p->n_probes) + 255) / 256);
+    tk::lat_finalise_kernel<<<grid, 256, 0, p->stream>>>(p->lat.S, p->lat.Lloc, p->nsegk, p->nchunk,
+                                                         p->prow, p->pcol, p->rowinfo, p->colinfo,
+                                                         state, p->probe_idx,
+                                                         probe_row ? p->n_probes : 0, probe_row);
+    p->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TK_OK;
+}
+
+double *next_probe_row(tk_plan *p)
+{
+    if (p->n_probes == 0 || p->probe_row >= p->probe_rows_cap) return nullptr;
+    return p->probe_series + (size_t)(p->probe_row++) * p->n_probes;
+}
+
+int set_probes(tk_plan *p, long long n_probes, const int64_t *idx, long long rows)
+{
+    p->n_probes = 0;
+    p->probe_row = 0;
+    if (p->probe_idx) { cudaFree(p->probe_idx); p->probe_idx = nullptr; }
+    if (p->probe_series) { cudaFree(p->probe_series); p->probe_series = nullptr; }
+    if (n_probes <= 0) return TK_OK;
+    std::vector<long long> h(n_probes);
+    for (long long i = 0; i < n_probes; ++i) {
+        TK_REQUIRE(idx[i] >= 0 && idx[i] < p->n, "probe index %lld out of range [0,%lld)",
+                   (long long)idx[i], p->n);
+        h[i] = idx[i] + p->state_off;
+    }
+    TK_CUDA(cudaMalloc((void **)&p->probe_idx, n_probes * sizeof(long long)));
+    TK_CUDA(cudaMemcpy(p->probe_idx, h.data(), n_probes * sizeof(long long), cudaMemcpyHostToDevice));
+    TK_CUDA(cudaMalloc((void **)&p->probe_series, (size_t)rows * n_probes * sizeof(double)));
+    p->n_probes = (int)n_probes;
+    p->probe_rows_cap = rows;
+    return TK_OK;
+}
+
+int graph_step(tk_plan *p, double coeff, double damping)
+{
+    const unsigned grid = (unsigned)((p->n + 255) / 256);
+    if (grid) {
+        tk::graph_step_kernel<<<grid, 256, 0, p->stream>>>(p->n, p->slice_off, p->ell_idx, p->deg,
+                                                          p->inv_mass, p->potential, p->buf[p->cur],
+                                                          p->buf[p->cur ^ 1], coeff, damping);
+        p->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    p->cur ^= 1;
+    if (double *row = next_probe_row(p)) {
+        tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(p->buf[p->cur], p->probe_idx,
+                                                                           row, p->n_probes);
+        p->launches++;
+        TK_CUDA(cudaGetLastError());
+    }
+    return TK_OK;
+}
+
+}  // namespace
+
+// ====================================================================================== ABI
+extern "C" {
+
+int tk_abi_version(void) { return TK_ABI_VERSION; }
+
+const char *tk_last_error(void) { return g_err.c_str(); }
+
+int tk_device_count(int *count)
+{
+    TK_REQUIRE(count, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return TK_OK;
+}
+
+int tk_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor,
+                   int64_t *total_mem_bytes)
+{
+    int rc = check_device(device);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    TK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) snprintf(name, name_len, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem_bytes) *total_mem_bytes = (int64_t)prop.totalGlobalMem;
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------------------ graph plan
+int tk_graph_plan_create(int device, int64_t n, const int64_t *rowptr, const int32_t *colidx,
+                         const double *degree, const double *inv_mass, const double *potential,
+                         tk_plan **out)
+{
+    TK_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    TK_REQUIRE(n >= 0 && n < 0x7fffffffLL, "n_nodes %lld out of range", (long long)n);
+    TK_REQUIRE(n == 0 || (rowptr && degree && inv_mass && potential), "NULL graph array");
+    int rc = check_device(device);
+    if (rc) return rc;
+    tk_plan *p = new tk_plan();
+    p->kind = kGraph;
+    p->n = n;
+    p->alloc = n + 1;  // +1: the always-zero slot that ELL padding points at
+#define TK_TRY(x)          \
+    do {                   \
+        rc = (x);          \
+        if (rc) {          \
+            tk_plan_destroy(p); \
+            return rc;     \
+        }                  \
+    } while (0)
+    TK_TRY(plan_common_init(p, device));
+    const long long nslice = (n + 31) / 32;
+    std::vector<long long> soff(nslice + 1, 0);
+    long long maxdeg = 0;
+    for (long long s = 0; s < nslice; ++s) {
+        long long wmax = 0;
+        for (long long i = s * 32; i < std::min<long long>(n, s * 32 + 32); ++i) {
+            const long long wd = rowptr[i + 1] - rowptr[i];
+            if (wd < 0) { tk_plan_destroy(p); return fail(TK_ERR_INVALID, "rowptr not monotone at %lld", i); }
+            wmax = std::max(wmax, wd);
+        }
+        soff[s + 1] = soff[s] + wmax * 32;
+    }
+    for (long long i = 0; i < n; ++i) maxdeg = std::max<long long>(maxdeg, (long long)degree[i]);
+    p->max_degree = maxdeg;
+    std::vector<int> ell((size_t)soff[nslice], (int)n);
+    for (long long i = 0; i < n; ++i) {
+        const long long s = i >> 5, lane = i & 31;
+        for (long long k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (colidx[k] < 0 || colidx[k] >= n) {
+                tk_plan_destroy(p);
+                return fail(TK_ERR_INVALID, "colidx[%lld]=%d out of range", k, colidx[k]);
+            }
+            ell[(size_t)(soff[s] + (k - rowptr[i]) * 32 + lane)] = colidx[k];
+        }
+    }
+    TK_TRY(plan_upload(p, &p->slice_off, soff));
+    TK_TRY(plan_upload(p, &p->ell_idx, ell));
+    TK_TRY(plan_upload(p, &p->deg, std::vector<double>(degree, degree + n)));
+    TK_TRY(plan_upload(p, &p->inv_mass, std::vector<double>(inv_mass, inv_mass + n)));
+    TK_TRY(plan_upload(p, &p->potential, std::vector<double>(potential, potential + n)));
+    TK_TRY(plan_alloc(p, &p->buf[0], (size_t)p->alloc, true));
+    TK_TRY(plan_alloc(p, &p->buf[1], (size_t)p->alloc, true));
+    *out = p;
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------------------ lattice plan
+int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
+{
+    TK_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    TK_REQUIRE(d, "desc is NULL");
+    TK_REQUIRE(d->size >= 1 && d->layers >= 1, "size and layers must be >= 1");
+    TK_REQUIRE(0 <= d->z_begin && d->z_begin < d->z_end && d->z_end <= d->layers,
+               "slab [%d,%d) not inside [0,%d)", d->z_begin, d->z_end, d->layers);
+    TK_REQUIRE(d->n_special == 0 || (d->special_index && d->special_flags), "special arrays NULL");
+    TK_REQUIRE(d->n_corr == 0 || (d->corr_a && d->corr_b && d->corr_sign), "corr arrays NULL");
+    int rc = check_device(device);
+    if (rc) return rc;
+
+    const long long S = d->size, L = d->layers, zb = d->z_begin, ze = d->z_end, Lloc = ze - zb;
+    const long long halo = L > 1 ? 1 : 0;
+    const long long plane = S * S * 4, planes = Lloc + 2 * halo;
+    const int ntab = (int)((S + tk::kTabSeg - 1) / tk::kTabSeg);
+
+    tk_plan *p = new tk_plan();
+    p->kind = kLattice;
+    p->n = Lloc * plane;
+    p->alloc = planes * plane;
+    p->state_off = halo * plane;
+    p->layers_global = (int)L;
+    p->z_begin = (int)zb;
+    TK_TRY(plan_common_init(p, device));
+
+    // ---- sparse defect description -> per-cell bits
+    struct CellBits { unsigned char part = 0xF, alive = 0xF; };
+    std::unordered_map<long long, CellBits> cells;            // key: global cell index (z*S+r)*S+c
+    std::unordered_map<long long, std::pair<double, double>> attrs;  // key: global node index
+    for (long long i = 0; i < d->n_special; ++i) {
+        const long long g = d->special_index[i];
+        if (g < 0 || g >= L * plane) { tk_plan_destroy(p); return fail(TK_ERR_INVALID, "special_index[%lld]=%lld out of range", i, g); }
+        const long long z = g / plane;
+        if (z < zb - 1 || z > ze) continue;  // irrelevant to this slab
+        const int q = (int)(g & 3);
+        const unsigned char fl = d->special_flags[i];
+        const bool alive = fl & 1, part = (fl & 2) && alive;
+        if (!alive || !part) {
+            CellBits &cb = cells[g >> 2];
+            if (!alive) cb.alive &= ~(1u << q);
+            if (!part) cb.part &= ~(1u << q);
+        }
+        const double im = d->special_inv_mass ? d->special_inv_mass[i] : 1.0;
+        const double v = d->special_potential ? d->special_potential[i] : 0.0;
+        if (alive && (im != 1.0 || v != 0.0) && z >= zb && z < ze) attrs[g] = {im, v};
+    }
+    auto cell_bits = [&](long long z, long long r, long long c) -> CellBits {
+        auto it = cells.find((z * S + r) * S + c);
+        return it == cells.end() ? CellBits() : it->second;
+    };
+
+    // ---- participation counts (static) and removed-node list
+    std::vector<double> rowinfo((size_t)Lloc * S * 8, 0.0), colinfo((size_t)Lloc * S * 8, 0.0);
+    for (long long zl = 0; zl < Lloc; ++zl)
+        for (long long x = 0; x < S; ++x)
+            for (int q = 0; q < 4; ++q) {
+                rowinfo[(size_t)(zl * S + x) * 8 + 4 + q] = (double)S;
+                colinfo[(size_t)(zl * S + x) * 8 + 4 + q] = (double)S;
+            }
+    for (const auto &kv : cells) {
+        const long long cellg = kv.first, z = cellg / (S * S);
+        if (z < zb || z >= ze) continue;
+        const long long r = (cellg / S) % S, c = cellg % S, zl = z - zb;
+        for (int q = 0; q < 4; ++q) {
+            if (!((kv.second.part >> q) & 1)) {
+                rowinfo[(size_t)(zl * S + r) * 8 + 4 + q] -= 1.0;
+                colinfo[(size_t)(zl * S + c) * 8 + 4 + q] -= 1.0;
+            }
+            if (!((kv.second.alive >> q) & 1)) p->dead_local.push_back(((zl * S + r) * S + c) * 4 + q);
+        }
+    }
+    std::sort(p->dead_local.begin(), p->dead_local.end());
+
+    // ---- corrections: global -> padded-local, sorted by receiving node
+    struct Corr { long long a, b; double s; };
+    std::vector<Corr> corr;
+    auto to_padded = [&](long long g, long long *outp) -> bool {
+        const long long z = g / plane;
+        if (z < zb - 1 || z > ze || (halo == 0 && z != 0)) return false;
+        *outp = g - zb * plane + halo * plane;
+        return true;
+    };
+    for (long long i = 0; i < d->n_corr; ++i) {
+        const long long a = d->corr_a[i], b = d->corr_b[i];
+        if (a < 0 || a >= L * plane || b < 0 || b >= L * plane) { tk_plan_destroy(p); return fail(TK_ERR_INVALID, "corr index out of range"); }
+        const long long za = a / plane;
+        if (za < zb || za >= ze) continue;
+        long long pa, pb;
+        if (!to_padded(a, &pa) || !to_padded(b, &pb)) {
+            tk_plan_destroy(p);
+            return fail(TK_ERR_INVALID, "edge correction %lld->%lld reaches beyond the slab halo", a, b);
+        }
+        corr.push_back({pa, pb, d->corr_sign[i]});
+    }
+    std::sort(corr.begin(), corr.end(), [](const Corr &x, const Corr &y) { return x.a < y.a; });
+
+    // ---- flagged table segments
+    auto segkey = [&](long long zl, long long r, long long c) { return (zl * S + r) * ntab + c / tk::kTabSeg; };
+    std::vector<long long> keys;
+    for (const auto &kv : cells) {
+        const long long cellg = kv.first, z = cellg / (S * S), r = (cellg / S) % S, c = cellg % S;
+        for (long long dz = -1; dz <= 1; ++dz) {
+            const long long zl = z + dz - zb;
+            if (zl >= 0 && zl < Lloc) keys.push_back(segkey(zl, r, c));
+        }
+    }
+    for (const auto &kv : attrs) {
+        const long long cellg = kv.first >> 2;
+        keys.push_back(segkey(cellg / (S * S) - zb, (cellg / S) % S, cellg % S));
+    }
+    for (const Corr &c : corr) {
+        const long long cellp = c.a >> 2;  // padded-local cell
+        keys.push_back(segkey(cellp / (S * S) - halo, (cellp / S) % S, cellp % S));
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const size_t ndet = keys.size();
+
+    std::vector<int> seg_flag((size_t)Lloc * S * ntab, -1);
+    std::vector<unsigned short> det_flags(ndet * tk::kTabSeg, 0);
+    std::vector<int> det_attr(ndet, -1);
+    std::vector<int2> det_corr(ndet, make_int2(0, 0));
+    std::vector<double> attr_im, attr_v;
+    size_t ci = 0;
+    for (size_t k = 0; k < ndet; ++k) {
+        const long long key = keys[k];
+        seg_flag[(size_t)key] = (int)k;
+        const long long tab = key % ntab, zr = key / ntab, r = zr % S, zl = zr / S, z = zl + zb;
+        bool any_attr = false;
+        for (int cc = 0; cc < tk::kTabSeg; ++cc) {
+            const long long c = tab * tk::kTabSeg + cc;
+            if (c >= S) continue;
+            const CellBits me = cell_bits(z, r, c);
+            unsigned f = (unsigned)me.part | ((unsigned)me.alive << 4);
+            if (z - 1 >= 0) f |= (unsigned)cell_bits(z - 1, r, c).part << 8;
+            if (z + 1 < L) f |= (unsigned)cell_bits(z + 1, r, c).part << 12;
+            det_flags[k * tk::kTabSeg + cc] = (unsigned short)f;
+            for (int q = 0; q < 4 && !any_attr; ++q)
+                if (attrs.count((((z * S + r) * S + c) << 2) + q)) any_attr = true;
+        }
+        if (any_attr) {
+            det_attr[k] = (int)(attr_im.size() / 256);
+            attr_im.resize(attr_im.size() + 256, 1.0);
+            attr_v.resize(attr_v.size() + 256, 0.0);
+            for (int cc = 0; cc < tk::kTabSeg && tab * tk::kTabSeg + cc < S; ++cc)
+                for (int q = 0; q < 4; ++q) {
+                    auto it = attrs.find(((((z * S + r) * S + tab * tk::kTabSeg + cc)) << 2) + q);
+                    if (it != attrs.end()) {
+                        attr_im[attr_im.size() - 256 + cc * 4 + q] = it->second.first;
+                        attr_v[attr_v.size() - 256 + cc * 4 + q] = it->second.second;
+                    }
+                }
+        }
+        // corrections whose receiving node lies in this segment (corr is sorted by a, and the
+        // padded node order follows (zl, r, c), i.e. the key order)
+        const long long lo = ((((zl + halo) * S + r) * S) + tab * tk::kTabSeg) * 4;
+        const long long hi = lo + tk::kTabSeg * 4;
+        while (ci < corr.size() && corr[ci].a < lo) ++ci;
+        size_t cj = ci;
+        while (cj < corr.size() && corr[cj].a < hi) ++cj;
+        det_corr[k] = make_int2((int)ci, (int)cj);
+    }
+    std::vector<long long> ca(corr.size()), cb(corr.size());
+    std::vector<double> cs(corr.size());
+    for (size_t i = 0; i < corr.size(); ++i) { ca[i] = corr[i].a; cb[i] = corr[i].b; cs[i] = corr[i].s; }
+
+    // ---- kernel variant + tiling
+    p->cpl = env_int("TK_LAT_CPL", 1);
+    p->wc = env_int("TK_LAT_WC", halo ? 1 : 8);
+    if (p->cpl != 1 && p->cpl != 2 && p->cpl != 4) p->cpl = 2;
+    const int nsegk_max = (int)((S + 31) / 32);
+    p->nsegk = (int)((S + 32 * p->cpl - 1) / (32 * p->cpl));
+    {
+        // rows per CTA: trade the column-partial traffic (16/rchunk B per update) against wave
+        // quantisation on (SMs x resident CTAs) slots
+        const int wz = 8 / p->wc;
+        const long long nct = (p->nsegk + p->wc - 1) / p->wc, nzg = (Lloc + wz - 1) / wz;
+        const long long slots = (long long)p->sm_count * 3;
+        int best = 16;
+        double best_eff = -1.0;
+        for (int rc_ = 16; rc_ <= 256; rc_ *= 2) {
+            const long long tiles = ((S + rc_ - 1) / rc_) * nct * nzg;
+            const long long waves = (tiles + slots - 1) / slots;
+            const double eff = (double)tiles / (double)(waves * slots) * (24.0 / (24.0 + 16.0 / rc_));
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = rc_; }
+        }
+        p->rchunk = env_int("TK_LAT_RCHUNK", best);
+        if (p->rchunk < 1) p->rchunk = best;
+    }
+    p->nchunk = (int)((S + p->rchunk - 1) / p->rchunk);
+    const int nchunk_alloc = p->nchunk;
+
+    const int *d_seg_flag; const unsigned short *d_det_flags; const int *d_det_attr; const int2 *d_det_corr;
+    const double *d_attr_im, *d_attr_v; const long long *d_ca, *d_cb; const double *d_cs;
+    TK_TRY(plan_upload(p, const_cast<int **>(&d_seg_flag), seg_flag));
+    TK_TRY(plan_upload(p, const_cast<unsigned short **>(&d_det_flags), det_flags));
+    TK_TRY(plan_upload(p, const_cast<int **>(&d_det_attr), det_attr));
+    TK_TRY(plan_upload(p, const_cast<int2 **>(&d_det_corr), det_corr));
+    TK_TRY(plan_upload(p, const_cast<double **>(&d_attr_im), attr_im));
+    TK_TRY(plan_upload(p, const_cast<double **>(&d_attr_v), attr_v));
+    TK_TRY(plan_upload(p, const_cast<long long **>(&d_ca), ca));
+    TK_TRY(plan_upload(p, const_cast<long long **>(&d_cb), cb));
+    TK_TRY(plan_upload(p, const_cast<double **>(&d_cs), cs));
+    TK_TRY(plan_upload(p, &p->rowinfo, rowinfo));
+    TK_TRY(plan_upload(p, &p->colinfo, colinfo));
+    TK_TRY(plan_alloc(p, &p->prow, (size_t)Lloc * S * nsegk_max * 4, true));
+    TK_TRY(plan_alloc(p, &p->pcol, (size_t)Lloc * nchunk_alloc * S * 4, true));
+    TK_TRY(plan_alloc(p, &p->buf[0], (size_t)p->alloc, true));
+    TK_TRY(plan_alloc(p, &p->buf[1], (size_t)p->alloc, true));
+
+    tk::LatDev &P = p->lat;
+    P.S = (int)S; P.Lloc = (int)Lloc; P.halo = (int)halo; P.ntab = ntab;
+    P.has_below = zb > 0; P.has_above = ze < L;
+    P.seg_flag = d_seg_flag; P.det_flags = d_det_flags; P.det_attr = d_det_attr; P.det_corr = d_det_corr;
+    P.attr_im = d_attr_im; P.attr_v = d_attr_v; P.corr_a = d_ca; P.corr_b = d_cb; P.corr_sign = d_cs;
+    P.rowinfo = p->rowinfo; P.colinfo = p->colinfo;
+    *out = p;
+    return TK_OK;
+}
+#undef TK_TRY
+
+// ------------------------------------------------------------------------------ common
+int tk_plan_set_stream(tk_plan *p, void *cuda_stream)
+{
+    TK_REQUIRE(p, "plan is NULL");
+    TK_CUDA(cudaSetDevice(p->device));
+    if (p->own_stream && p->stream) {
+        TK_CUDA(cudaStreamSynchronize(p->stream));
+        TK_CUDA(cudaStreamDestroy(p->stream));
+    }
+    p->stream = (cudaStream_t)cuda_stream;
+    p->own_stream = false;
+    return TK_OK;
+}
+
+int tk_plan_num_nodes(const tk_plan *p, int64_t *n)
+{
+    TK_REQUIRE(p && n, "NULL argument");
+    *n = p->n;
+    return TK_OK;
+}
+
+int tk_plan_max_degree(tk_plan *p, int64_t *max_degree)
+{
+    TK_REQUIRE(p && max_degree, "NULL argument");
+    if (p->max_degree < 0) {
+        TK_CUDA(cudaSetDevice(p->device));
+        int *d_out = nullptr;
+        TK_CUDA(cudaMalloc((void **)&d_out, sizeof(int)));
+        TK_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int), p->stream));
+        tk::lat_maxdeg_kernel<<<p->sm_count * 8, 256, 0, p->stream>>>(p->lat, d_out);
+        p->launches++;
+        int h = 0;
+        cudaError_t e = cudaMemcpyAsync(&h, d_out, sizeof(int), cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        cudaFree(d_out);
+        TK_CUDA(e);
+        p->max_degree = h;
+    }
+    *max_degree = p->max_degree;
+    return TK_OK;
+}
+
+int tk_plan_set_state_sparse(tk_plan *p, int64_t n, const int64_t *index, const double *value)
+{
+    TK_REQUIRE(p, "plan is NULL");
+    TK_REQUIRE(n == 0 || (index && value), "NULL kick arrays");
+    TK_CUDA(cudaSetDevice(p->device));
+    TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * sizeof(double), p->stream));
+    TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * sizeof(double), p->stream));
+    p->cur = 0;
+    if (n > 0) {
+        std::vector<long long> h(n);
+        for (int64_t i = 0; i < n; ++i) {
+            TK_REQUIRE(index[i] >= 0 && index[i] < p->n, "kick index %lld out of range [0,%lld)",
+                       (long long)index[i], p->n);
+            h[i] = index[i] + p->state_off;
+        }
+        long long *d_idx = nullptr;
+        double *d_val = nullptr;
+        TK_CUDA(cudaMalloc((void **)&d_idx, n * sizeof(long long)));
+        cudaError_t e = cudaMalloc((void **)&d_val, n * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, h.data(), n * sizeof(long long), cudaMemcpyHostToDevice, p->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, value, n * sizeof(double), cudaMemcpyHostToDevice, p->stream);
+        if (e == cudaSuccess) {
+            tk::scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(p->buf[0], d_idx, d_val, n);
+            p->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        cudaFree(d_idx);
+        cudaFree(d_val);
+        TK_CUDA(e);
+    }
+    return TK_OK;
+}
+
+int tk_plan_set_state(tk_plan *p, const double *u, const double *u_prev)
+{
+    TK_REQUIRE(p && u, "NULL argument");
+    TK_CUDA(cudaSetDevice(p->device));
+    TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * sizeof(double), p->stream));
+    TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * sizeof(double), p->stream));
+    p->cur = 0;
+    TK_CUDA(cudaMemcpyAsync(p->buf[0] + p->state_off, u, (size_t)p->n * sizeof(double),
+                            cudaMemcpyHostToDevice, p->stream));
+    if (u_prev)
+        TK_CUDA(cudaMemcpyAsync(p->buf[1] + p->state_off, u_prev, (size_t)p->n * sizeof(double),
+                                cudaMemcpyHostToDevice, p->stream));
+    if (!p->dead_local.empty()) {  // removed nodes never carry amplitude
+        const long long nd = (long long)p->dead_local.size();
+        std::vector<long long> h(nd);
+        for (long long i = 0; i < nd; ++i) h[i] = p->dead_local[i] + p->state_off;
+        std::vector<double> z(nd, 0.0);
+        long long *d_idx = nullptr;
+        double *d_val = nullptr;
+        TK_CUDA(cudaMalloc((void **)&d_idx, nd * sizeof(long long)));
+        cudaError_t e = cudaMalloc((void **)&d_val, nd * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, h.data(), nd * sizeof(long long), cudaMemcpyHostToDevice, p->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, z.data(), nd * sizeof(double), cudaMemcpyHostToDevice, p->stream);
+        if (e == cudaSuccess) {
+            const unsigned g = (unsigned)((nd + 255) / 256);
+            tk::scatter_kernel<<<g, 256, 0, p->stream>>>(p->buf[0], d_idx, d_val, nd);
+            tk::scatter_kernel<<<g, 256, 0, p->stream>>>(p->buf[1], d_idx, d_val, nd);
+            p->launches += 2;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        cudaFree(d_idx);
+        cudaFree(d_val);
+        TK_CUDA(e);
+    }
+    TK_CUDA(cudaStreamSynchronize(p->stream));
+    return TK_OK;
+}
+
+int tk_plan_get_state(tk_plan *p, double *u, double *u_prev)
+{
+    TK_REQUIRE(p, "plan is NULL");
+    TK_CUDA(cudaSetDevice(p->device));
+    if (u)
+        TK_CUDA(cudaMemcpyAsync(u, p->buf[p->cur] + p->state_off, (size_t)p->n * sizeof(double),
+                                cudaMemcpyDeviceToHost, p->stream));
+    if (u_prev)
+        TK_CUDA(cudaMemcpyAsync(u_prev, p->buf[p->cur ^ 1] + p->state_off, (size_t)p->n * sizeof(double),
+                                cudaMemcpyDeviceToHost, p->stream));
+    TK_CUDA(cudaStreamSynchronize(p->stream));
+    return TK_OK;
+}
+
+int tk_lattice_halo_ptrs(tk_plan *p, int32_t next_state, void **send_lo, void **send_hi,
+                         void **recv_lo, void **recv_hi, int64_t *plane_bytes)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    TK_REQUIRE(p->lat.halo, "2-D sheets have no halo planes");
+    const size_t plane = (size_t)p->lat.S * p->lat.S * 4;
+    double *b = p->buf[next_state ? (p->cur ^ 1) : p->cur];
+    if (recv_lo) *recv_lo = b;
+    if (send_lo) *send_lo = b + plane;
+    if (send_hi) *send_hi = b + plane * p->lat.Lloc;
+    if (recv_hi) *recv_hi = b + plane * (p->lat.Lloc + 1);
+    if (plane_bytes) *plane_bytes = (int64_t)(plane * sizeof(double));
+    return TK_OK;
+}
+
+int tk_lattice_step_begin(tk_plan *p, double coeff, double damping)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    TK_CUDA(cudaSetDevice(p->device));
+    p->coeff = coeff;
+    p->damping = damping;
+    int rc = launch_lat_dispatch<1>(p, 0, p->lat.Lloc);
+    if (rc) return rc;
+    return lat_finalise(p, p->buf[p->cur], next_probe_row(p));
+}
+
+int tk_lattice_step_layers(tk_plan *p, int32_t zl_begin, int32_t zl_end)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    TK_REQUIRE(0 <= zl_begin && zl_begin <= zl_end && zl_end <= p->lat.Lloc, "bad layer range");
+    return launch_lat_dispatch<0>(p, zl_begin, zl_end);
+}
+
+int tk_lattice_step_end(tk_plan *p)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    p->cur ^= 1;
+    return lat_finalise(p, p->buf[p->cur], next_probe_row(p));
+}
+
+int tk_plan_run(tk_plan *p, const tk_run_args *a)
+{
+    TK_REQUIRE(p && a, "NULL argument");
+    TK_REQUIRE(a->steps >= 0, "steps must be >= 0");
+    TK_REQUIRE(a->n_probes == 0 || (a->probe_index && a->probe_out), "probe arrays NULL");
+    TK_REQUIRE(a->energy_out == nullptr, "energy series not implemented in this ABI version");
+    TK_CUDA(cudaSetDevice(p->device));
+    int rc = set_probes(p, a->n_probes, a->probe_index, a->steps + 1);
+    if (rc) return rc;
+
+    // optional full history (physics.py:104,129), staged through a bounded device buffer
+    const size_t row_bytes = (size_t)p->n * sizeof(double);
+    long long chunk_rows = 0;
+    double *d_hist = nullptr;
+    if (a->history_out && p->n > 0) {
+        chunk_rows = std::max<long long>(1, std::min<long long>(a->steps + 1, (long long)(kHistoryChunkBytes / row_bytes)));
+        TK_CUDA(cudaMalloc((void **)&d_hist, (size_t)chunk_rows * row_bytes));
+    }
+    long long hist_fill = 0, hist_done = 0;
+    auto record = [&]() -> cudaError_t {
+        if (!d_hist) return cudaSuccess;
+        cudaError_t e = cudaMemcpyAsync(d_hist + (size_t)hist_fill * p->n, p->buf[p->cur] + p->state_off,
+                                        row_bytes, cudaMemcpyDeviceToDevice, p->stream);
+        if (e != cudaSuccess) return e;
+        if (++hist_fill == chunk_rows) {
+            e = cudaMemcpyAsync(a->history_out + (size_t)hist_done * p->n, d_hist,
+                                (size_t)hist_fill * row_bytes, cudaMemcpyDeviceToHost, p->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+            hist_done += hist_fill;
+            hist_fill = 0;
+        }
+        return e;
+    };
+#define TK_RUN_TRY(x)                \
+    do {                             \
+        rc = (x);                    \
+        if (rc) {                    \
+            if (d_hist) cudaFree(d_hist); \
+            return rc;               \
+        }                            \
+    } while (0)
+#define TK_RUN_CUDA(x)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (x);                                                                 \
+        if (e_ != cudaSuccess) {                                                              \
+            if (d_hist) cudaFree(d_hist);                                                     \
+            return fail(TK_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));            \
+        }                                                                                     \
+    } while (0)
+
+    std::vector<cudaEvent_t> kev;  // pairs around each step kernel (bounded pool)
+    if (a->step_kernel_ms) {
+        const int64_t pairs = std::min<int64_t>(a->steps, 4096);
+        kev.resize((size_t)pairs * 2, nullptr);
+        for (auto &e : kev) TK_RUN_CUDA(cudaEventCreate(&e));
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (a->elapsed_ms) {
+        TK_RUN_CUDA(cudaEventCreate(&ev0));
+        TK_RUN_CUDA(cudaEventCreate(&ev1));
+    }
+    if (p->kind == kGraph) {
+        if (double *row = next_probe_row(p)) {
+            tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(p->buf[p->cur], p->probe_idx, row, p->n_probes);
+            p->launches++;
+        }
+        TK_RUN_CUDA(record());
+        if (ev0) TK_RUN_CUDA(cudaEventRecord(ev0, p->stream));
+        for (int64_t s = 0; s < a->steps; ++s) {
+            const bool tk_ = (size_t)(2 * s + 1) < kev.size();
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s], p->stream));
+            TK_RUN_TRY(graph_step(p, a->coeff, a->damping));
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s + 1], p->stream));
+            TK_RUN_CUDA(record());
+        }
+    } else {
+        TK_RUN_TRY(tk_lattice_step_begin(p, a->coeff, a->damping));
+        TK_RUN_CUDA(record());
+        if (ev0) TK_RUN_CUDA(cudaEventRecord(ev0, p->stream));
+        for (int64_t s = 0; s < a->steps; ++s) {
+            const bool tk_ = (size_t)(2 * s + 1) < kev.size();
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s], p->stream));
+            TK_RUN_TRY(launch_lat_dispatch<0>(p, 0, p->lat.Lloc));
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s + 1], p->stream));
+            TK_RUN_TRY(tk_lattice_step_end(p));
+            TK_RUN_CUDA(record());
+        }
+    }
+    if (ev1) TK_RUN_CUDA(cudaEventRecord(ev1, p->stream));
+    if (d_hist && hist_fill > 0)
+        TK_RUN_CUDA(cudaMemcpyAsync(a->history_out + (size_t)hist_done * p->n, d_hist,
+                                    (size_t)hist_fill * row_bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (p->n_probes > 0)
+        TK_RUN_CUDA(cudaMemcpyAsync(a->probe_out, p->probe_series,
+                                    (size_t)(a->steps + 1) * p->n_probes * sizeof(double),
+                                    cudaMemcpyDeviceToHost, p->stream));
+    TK_RUN_CUDA(cudaStreamSynchronize(p->stream));
+    if (a->elapsed_ms) {
+        float ms = 0.f;
+        TK_RUN_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        *a->elapsed_ms = (double)ms;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    if (a->step_kernel_ms) {
+        double total = 0.0;
+        for (size_t i = 0; i + 1 < kev.size(); i += 2) {
+            float ms = 0.f;
+            TK_RUN_CUDA(cudaEventElapsedTime(&ms, kev[i], kev[i + 1]));
+            total += ms;
+        }
+        // scale to all steps if the pool was smaller than the step count
+        if (!kev.empty()) total *= (double)a->steps / (double)(kev.size() / 2);
+        *a->step_kernel_ms = total;
+        for (auto &e : kev) cudaEventDestroy(e);
+    }
+    if (d_hist) cudaFree(d_hist);
+    return TK_OK;
+#undef TK_RUN_TRY
+#undef TK_RUN_CUDA
+}
+
+int tk_plan_launch_count(const tk_plan *p, int64_t *launches)
+{
+    TK_REQUIRE(p && launches, "NULL argument");
+    *launches = p->launches;
+    return TK_OK;
+}
+
+int tk_plan_destroy(tk_plan *p)
+{
+    if (!p) return TK_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (void *q : p->owned) cudaFree(q);
+    if (p->probe_idx) cudaFree(p->probe_idx);
+    if (p->probe_series) cudaFree(p->probe_series);
+    if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------------------ DFT
+int tk_dft_abs(int device, const double *series, int64_t batch, int64_t n, double *spectrum,
+               int64_t *argmax)
+{
+    TK_REQUIRE(series && spectrum, "NULL argument");
+    TK_REQUIRE(batch >= 1 && batch <= 65535 && n >= 1 && n < 0x7fffffffLL, "bad batch/n");
+    int rc = check_device(device);
+    if (rc) return rc;
+    double *d_x = nullptr, *d_s = nullptr;
+    long long *d_a = nullptr;
+    const size_t bytes = (size_t)batch * n * sizeof(double);
+    cudaError_t e = cudaMalloc((void **)&d_x, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_s, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_a, batch * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemcpy(d_x, series, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        tk::dft_abs_kernel<<<dim3((unsigned)n, (unsigned)batch), 128>>>(d_x, n, d_s);
+        tk::argmax_kernel<<<(unsigned)batch, 256>>>(d_s, n, d_a);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(spectrum, d_s, bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && argmax) {
+        static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+        e = cudaMemcpy(argmax, d_a, batch * sizeof(long long), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_x);
+    cudaFree(d_s);
+    cudaFree(d_a);
+    TK_CUDA(e);
+    return TK_OK;
+}
+
+}  // extern "C"

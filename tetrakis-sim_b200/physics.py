@@ -1,0 +1,271 @@
+"""Drop-in ``run_wave_sim`` / ``run_fft`` / ``SimulationHistory`` on the B200.
+
+Mirrors ``tetrakis_sim/physics.py`` of the reference: same names, argument meaning, defaults,
+metadata keys, warning category and text, exceptions.  The stepping itself
+(``physics.py:104-129``) and the spectrum (``physics.py:162-163``) run on the device through the
+C ABI in ``include/tetrakis_b200.h``; there is no CPU fallback (missing library or device =>
+exception).
+
+Extra keyword-only arguments (all optional; the positional signature is the reference's):
+  device   CUDA device ordinal (default 0)
+  path     "auto" | "graph" | "structured".  "graph" is the sliced-ELL kernel that reproduces the
+           reference bit for bit on any networkx graph; "structured" the clique-sum kernel
+           (always used for a LatticeSpec).  "auto" = graph for networkx input.
+  record   "all" (default for graphs: every state, as the reference returns) or "probes"
+           (default for a LatticeSpec: only the probe nodes' time series and the final state).
+  probes   nodes to record when record="probes" (default: the kicked nodes)
+"""
+
+from __future__ import annotations
+
+import warnings
+from collections.abc import Hashable, Iterable, Mapping
+
+import numpy as np
+
+from . import _lib
+from .compiler import CompiledGraph, compile_graph, compile_lattice, structured_from_graph
+from .lattice import LatticeSpec
+
+_EAGER_DICT_LIMIT = 2_000_000  # (steps+1)*N entries above this -> lazy row views instead of dicts
+
+
+class SimulationHistory(list):
+    """List-like container returned by :func:`run_wave_sim` (reference physics.py:13-27)."""
+
+    def __init__(
+        self,
+        states: Iterable[Mapping[Hashable, float]],
+        *,
+        dt: float,
+        wave_speed: float,
+        metadata: dict | None = None,
+    ) -> None:
+        super().__init__(states)
+        self.dt = dt
+        self.wave_speed = wave_speed
+        self.metadata = metadata or {}
+        # device-run extras (absent on histories built by hand)
+        self.array: np.ndarray | None = None  # (steps+1, N) in node order, when record="all"
+        self.nodes: list | None = None
+        self.probe_nodes: list | None = None
+        self.probe_series: np.ndarray | None = None  # (steps+1, n_probes)
+        self.final_state: np.ndarray | None = None
+        self.elapsed_ms: float | None = None
+        self._index: dict | None = None  # node -> column of ``array``
+
+
+class _RowView(Mapping):
+    """One recorded state as a read-only mapping node -> value over a row of the history array."""
+
+    __slots__ = ("_row", "_index", "_nodes", "_extra")
+
+    def __init__(self, row, index, nodes, extra=None):
+        self._row, self._index, self._nodes, self._extra = row, index, nodes, extra
+
+    def __getitem__(self, node):
+        i = self._index.get(node)
+        if i is None:
+            if self._extra and node in self._extra:
+                return self._extra[node]
+            raise KeyError(node)
+        return float(self._row[i])
+
+    def __iter__(self):
+        yield from self._nodes
+        if self._extra:
+            yield from self._extra
+
+    def __len__(self):
+        return len(self._nodes) + (len(self._extra) if self._extra else 0)
+
+    def values(self):
+        vals = self._row.tolist()
+        if self._extra:
+            vals += list(self._extra.values())
+        return vals
+
+    def copy(self):
+        return dict(self.items())
+
+
+def _cfl(max_degree: int, c: float, dt: float, steps: int, damping: float):
+    """reference physics.py:64-91: metadata + CFL clamp.  Returns (effective_dt, metadata)."""
+    effective_dt = float(dt)
+    metadata: dict = {
+        "steps": steps,
+        "requested_dt": dt,
+        "wave_speed": c,
+        "max_degree": max_degree,
+        "damping": damping,
+    }
+    if max_degree > 0 and c > 0.0:
+        cfl_limit = float(1.0 / np.sqrt(max_degree))
+        metadata["stability_limit"] = cfl_limit
+        if c * effective_dt > cfl_limit:
+            effective_dt = cfl_limit / c
+            metadata["stability_adjusted"] = True
+            metadata["effective_dt"] = float(effective_dt)
+            warnings.warn(
+                (
+                    "Requested time-step is unstable for the current lattice "
+                    f"(c*dt={c * dt:.3f} > {cfl_limit:.3f}). Clamping dt to "
+                    f"{effective_dt:.3f}"
+                ),
+                RuntimeWarning,
+                stacklevel=4,
+            )
+    metadata.setdefault("stability_adjusted", False)
+    metadata.setdefault("effective_dt", float(effective_dt))
+    return effective_dt, metadata
+
+
+def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes):
+    comp: CompiledGraph
+    if path == "structured":
+        comp = structured_from_graph(G, device=device)
+    else:
+        comp = compile_graph(G, device=device)
+    try:
+        nodes, index = comp.nodes, comp.index
+        effective_dt, metadata = _cfl(comp.max_degree, c, dt, steps, damping)
+        # physics.py:30-38: zero state, then the user's kicks, else a unit kick at nodes[len//2]
+        extra0 = None
+        if initial_data:
+            kicks = {n: float(v) for n, v in initial_data.items() if n in index}
+            extra0 = {n: v for n, v in initial_data.items() if n not in index} or None
+        elif nodes:
+            kicks = {nodes[len(nodes) // 2]: 1.0}
+        else:
+            kicks = {}
+        to_state = (lambda i: i) if comp.state_index is None else (lambda i: int(comp.state_index[i]))
+        comp.plan.set_state_sparse([to_state(index[n]) for n in kicks], list(kicks.values()))
+        coeff = (c * effective_dt) ** 2  # physics.py:105
+        n = len(nodes)
+        if record == "all":
+            out = comp.plan.run(steps, coeff, damping, history=True, timed=True)
+            arr = out["history"]
+            if comp.state_index is not None:
+                arr = np.ascontiguousarray(arr[:, comp.state_index])
+            if (steps + 1) * n <= _EAGER_DICT_LIMIT:
+                states = [dict(zip(nodes, row)) for row in arr.tolist()]
+                if extra0:
+                    states[0].update(extra0)
+            else:
+                states = [_RowView(arr[t], index, nodes, extra0 if t == 0 else None)
+                          for t in range(steps + 1)]  # fmt: skip
+            hist = SimulationHistory(states, dt=effective_dt, wave_speed=c, metadata=metadata)
+            hist.array, hist.nodes, hist._index = arr, nodes, index
+            hist.final_state = arr[-1]
+        else:
+            pnodes = list(probes) if probes is not None else list(kicks)
+            pidx = [to_state(index[p]) for p in pnodes]
+            out = comp.plan.run(steps, coeff, damping, probes=pidx, timed=True)
+            series = out["probes"] if pidx else np.empty((steps + 1, 0))
+            states = [dict(zip(pnodes, row)) for row in series.tolist()]
+            hist = SimulationHistory(states, dt=effective_dt, wave_speed=c, metadata=metadata)
+            hist.probe_nodes, hist.probe_series, hist.nodes = pnodes, series, nodes
+            fin = comp.plan.get_state()
+            hist.final_state = fin if comp.state_index is None else fin[comp.state_index]
+        hist.elapsed_ms = out["elapsed_ms"]
+        return hist
+    finally:
+        comp.plan.close()
+
+
+def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device, record, probes):
+    plan = compile_lattice(spec, device=device)
+    try:
+        effective_dt, metadata = _cfl(plan.max_degree, c, dt, steps, damping)
+        if initial_data:
+            kicks = {n: float(v) for n, v in initial_data.items() if spec.contains(n)}
+        else:
+            kicks = {spec.node(spec.default_node_index()): 1.0}
+        plan.set_state_sparse([spec.index(n) for n in kicks], list(kicks.values()))
+        coeff = (c * effective_dt) ** 2
+        pnodes = list(probes) if probes is not None else list(kicks)
+        pidx = [spec.index(p) for p in pnodes]
+        if record == "all":
+            out = plan.run(steps, coeff, damping, probes=pidx, history=True, timed=True)
+        else:
+            out = plan.run(steps, coeff, damping, probes=pidx, timed=True)
+        series = out["probes"] if pidx else np.empty((steps + 1, 0))
+        states = [dict(zip(pnodes, row)) for row in series.tolist()]
+        hist = SimulationHistory(states, dt=effective_dt, wave_speed=c, metadata=metadata)
+        hist.probe_nodes, hist.probe_series = pnodes, series
+        hist.array = out["history"]  # (steps+1, num_slots) in device layout when record="all"
+        hist.final_state = hist.array[-1] if hist.array is not None else plan.get_state()
+        hist.elapsed_ms = out["elapsed_ms"]
+        hist.metadata["launches"] = plan.launches
+        return hist
+    finally:
+        plan.close()
+
+
+def run_wave_sim(
+    G,
+    steps: int = 100,
+    initial_data: dict | None = None,
+    c: float = 1.0,
+    dt: float = 0.2,
+    damping: float = 0.0,
+    *,
+    device: int = 0,
+    path: str = "auto",
+    record: str | None = None,
+    probes: list | None = None,
+) -> SimulationHistory:
+    """Simulate the discrete wave equation on ``G`` (reference physics.py:41-131).
+
+    ``G`` is a ``networkx`` graph (not mutated) or a :class:`LatticeSpec`.  The CFL check clamps an
+    unstable ``dt`` and emits a :class:`RuntimeWarning`, exactly as the reference does.
+    """
+    steps = int(steps)
+    if steps < 0:
+        steps = 0  # range(steps) in the reference simply does not iterate
+    if path not in ("auto", "graph", "structured"):
+        raise ValueError("path must be 'auto', 'graph' or 'structured'")
+    if isinstance(G, LatticeSpec):
+        return _run_lattice(G, steps, initial_data, c, dt, damping, device, record or "probes", probes)
+    return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes)
+
+
+def run_fft(
+    history: Iterable[Mapping[Hashable, float]],
+    node: Hashable | None = None,
+    *,
+    dt: float | None = None,
+    device: int = 0,
+) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Spectrum of one node across the history (reference physics.py:140-165).
+
+    Returns ``(freq, |X|, values)``; ``|X|`` is computed by the device DFT kernel, ``freq`` is
+    ``np.fft.fftfreq(len(values), d=dt)`` (pure index arithmetic)."""
+    history_list = list(history)
+    if not history_list:
+        raise ValueError("Simulation history is empty")
+    sample_state = history_list[0]
+    if node is None:
+        node = next(iter(sample_state.keys()))
+    inferred_dt = dt
+    if inferred_dt is None and hasattr(history, "dt"):
+        inferred_dt = history.dt
+    if inferred_dt is None:
+        inferred_dt = 1.0
+    values = None
+    arr, index = getattr(history, "array", None), getattr(history, "_index", None)
+    if arr is not None and index is not None and len(arr) == len(history_list):
+        col = index.get(node)  # a column of the recorded array instead of steps+1 dict lookups
+        if col is not None:
+            values = np.array(arr[:, col], dtype=np.float64)
+    if values is None:
+        values = np.array([state.get(node, 0.0) for state in history_list], dtype=np.float64)
+    spectrum, _ = _lib.dft_abs(values, device=device)
+    freq = np.fft.fftfreq(len(values), d=inferred_dt)
+    return freq, spectrum, values
+
+
+def dominant_frequency(freq, spectrum) -> float:
+    """``float(freq[np.argmax(spectrum)])`` (reference batch.py:205).  The sign is not meaningful
+    for a real signal: bins k and N-k tie up to rounding."""
+    return float(np.asarray(freq)[int(np.argmax(spectrum))])

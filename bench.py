@@ -45,7 +45,12 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    nvidia-smi takes a few hundred ms to start, so the sampler is started early (``start()``), the
+    caller brackets the timed region with ``mark_begin()`` / ``mark_end()``, and only rows that
+    arrived inside the bracket count (falling back to every row under load if the region was shorter
+    than one sampling period)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -55,23 +60,41 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            deadline = time.perf_counter() + 5.0
+            while not self.rows and time.perf_counter() < deadline:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def __enter__(self):
+        if self.proc is None:
+            self.start()
+        self.mark_begin()
+        return self
 
     def __exit__(self, *exc):
+        self.mark_end()
+        time.sleep(0.06)  # let the last sample of the region arrive
         if self.proc:
             self.proc.terminate()
             try:
@@ -80,12 +103,17 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        scope = "timed region"
+        if not inside:
+            inside, scope = [r for _, r in self.rows], "warm-up + timed region (region shorter than a sample)"
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for nm, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
@@ -94,7 +122,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw), "scope": scope}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -195,11 +223,12 @@ def gpu_single(args):
     n_updates = spec.num_nodes  # surviving nodes
     kidx = [spec.index(kick)]
 
+    clk = ClockSampler(0).start()
     plan.set_state_sparse(kidx, [1.0])
     plan.run(args.warmup, coeff, 0.0, probes=kidx)
     torch.cuda.synchronize()
     l0 = plan.launches
-    with ClockSampler(0) as clk:
+    with clk:
         out = plan.run(args.steps, coeff, 0.0, probes=kidx, timed=True)
         torch.cuda.synchronize()
     launches = plan.launches - l0
@@ -225,6 +254,7 @@ def gpu_single(args):
            "h2d_bytes_per_step": 16.0 / args.steps,
            "d2h_bytes_per_step": (final.nbytes + o2["probes"].nbytes) / args.steps,
            "seconds": e2e_s, "includes": "set_state_sparse + run + probe series D2H + final state D2H (pinned)"}
+    tiling = plan.tiling
     plan.close()
 
     cpu = cpu_run(workload, steps=10, warmup=1, budget_s=15.0) if not args.no_cpu else None
@@ -235,8 +265,7 @@ def gpu_single(args):
         "config": {"workload": workload, "lattice": desc, "nodes": n_updates, "max_degree": maxdeg,
                    "effective_dt": dt_eff, "kick": list(map(str, kick)),
                    "l2": f"state {2 * spec.num_slots * 8 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
-                   "kernel_variant": {k: os.environ.get(k) for k in ("TK_LAT_CPL", "TK_LAT_WC", "TK_LAT_RCHUNK")
-                                      if os.environ.get(k)}},
+                   "tiling": tiling},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "kernel": "lat_step_kernel", "bytes_per_update": BYTES_PER_UPDATE,

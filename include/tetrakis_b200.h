@@ -145,6 +145,11 @@ int tk_lattice_step_layers(tk_plan *plan, int32_t zl_begin, int32_t zl_end);
 /* After every layer was updated: finish the row/column sums of the new state, swap buffers. */
 int tk_lattice_step_end(tk_plan *plan);
 
+/* Tiling the lattice step kernel uses (diagnostics for bench.py): cells per lane, segments per
+ * CTA, rows per CTA, resident CTAs per SM.  Overridable with TK_LAT_CPL / TK_LAT_WC / TK_LAT_RCHUNK. */
+int tk_lattice_tiling(const tk_plan *plan, int32_t *cells_per_lane, int32_t *segs_per_cta,
+                      int32_t *rows_per_cta, int32_t *ctas_per_sm);
+
 /* ------------------------------------------------------------------------------------------
  * Probe spectrum: |DFT| of `batch` real series of length n (physics.py:162-163, np.fft.fft of a
  * real signal; n is arbitrary, steps+1 is never a power of two) and np.argmax of each

@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
     "tk_plan_run", "tk_plan_launch_count", "tk_plan_destroy",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
-    "tk_lattice_step_end", "tk_dft_abs",
+    "tk_lattice_step_end", "tk_lattice_tiling", "tk_dft_abs",
 )  # fmt: skip
 
 
@@ -97,6 +97,8 @@ def lib():
     L.tk_lattice_step_begin.argtypes = [P, c_double, c_double]
     L.tk_lattice_step_layers.argtypes = [P, c_int32, c_int32]
     L.tk_lattice_step_end.argtypes = [P]
+    L.tk_lattice_tiling.argtypes = [P, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
+                                    POINTER(c_int32)]  # fmt: skip
     L.tk_dft_abs.argtypes = [c_int, P, c_int64, c_int64, P, P]
     for name in ABI_SYMBOLS:
         fn = getattr(L, name)
@@ -224,6 +226,14 @@ class Plan:
         n = c_int64(0)
         check(lib().tk_plan_launch_count(self._h, ctypes.byref(n)))
         return n.value
+
+    @property
+    def tiling(self) -> dict:
+        a, b, c, d = c_int32(0), c_int32(0), c_int32(0), c_int32(0)
+        check(lib().tk_lattice_tiling(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
+                                      ctypes.byref(d)))  # fmt: skip
+        return {"cells_per_lane": a.value, "segs_per_cta": b.value, "rows_per_cta": c.value,
+                "ctas_per_sm": d.value}  # fmt: skip
 
     def set_stream(self, cuda_stream: int):
         check(lib().tk_plan_set_stream(self._h, c_void_p(cuda_stream)))

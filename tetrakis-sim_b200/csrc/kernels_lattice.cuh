@@ -261,35 +261,60 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
 
 // Deterministic finalise: fixed-order sums of the partials written by lat_step_kernel, plus the
 // probe gather (reference physics.py:162 reads one node per recorded state).
-//   threads [0, Lloc*S*4)            -> RowSum[zl][r][q]
-//   threads [Lloc*S*4, 2*Lloc*S*4)   -> ColSum[zl][c][q]
-//   first n_probes threads of block 0 also gather probes from the NEW state `state`.
+//   blocks [0, nrowblk)   : one WARP per (layer,row) line.  The line's partials are nsegk*4
+//                           contiguous doubles; lane l strides by 32 so it always meets quadrant
+//                           l&3, then lanes of equal quadrant are combined by a fixed butterfly.
+//   blocks [nrowblk, ...) : one THREAD per (layer, column, quadrant), summing over row chunks
+//                           (coalesced across columns).
+//   block 0 also gathers the probes from the NEW state.
 __global__ void __launch_bounds__(256)
-lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, const double *__restrict__ prow,
-                    const double *__restrict__ pcol, double *__restrict__ rowinfo,
-                    double *__restrict__ colinfo, const double *__restrict__ state,
-                    const long long *__restrict__ probe_idx, int n_probes,
-                    double *__restrict__ probe_row)
+lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, int nrowblk,
+                    const double *__restrict__ prow, const double *__restrict__ pcol,
+                    double *__restrict__ rowinfo, double *__restrict__ colinfo,
+                    const double *__restrict__ state, const long long *__restrict__ probe_idx,
+                    int n_probes, double *__restrict__ probe_row)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nline = (long long)Lloc * S * 4;
-    if (t < n_probes) probe_row[t] = state[probe_idx[t]];
-    if (t < nline) {
-        const long long line = t >> 2;
+    if (blockIdx.x == 0)
+        for (int t = threadIdx.x; t < n_probes; t += blockDim.x) probe_row[t] = state[probe_idx[t]];
+    const long long nline = (long long)Lloc * S;
+    if ((int)blockIdx.x < nrowblk) {
+        const int lane = threadIdx.x & 31;
+        const long long line = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+        if (line >= nline) return;
+        const double *p = prow + (size_t)line * nsegk * 4;
+        const int len = nsegk * 4;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = lane;
+        for (; i + 96 < len; i += 128) {
+            a0 += p[i];
+            a1 += p[i + 32];
+            a2 += p[i + 64];
+            a3 += p[i + 96];
+        }
+        for (; i < len; i += 32) a0 += p[i];
+        double acc = (a0 + a1) + (a2 + a3);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (lane < 4) rowinfo[line * 8 + lane] = acc;
+    } else {
+        const long long t = (long long)(blockIdx.x - nrowblk) * blockDim.x + threadIdx.x;
+        if (t >= nline * 4) return;
+        const long long line = t >> 2;  // zl*S + c
         const int q = (int)(t & 3);
-        const double *p = prow + (size_t)line * nsegk * 4 + q;
-        double acc = 0.0;
-        for (int s = 0; s < nsegk; ++s) acc += p[(size_t)s * 4];
-        rowinfo[line * 8 + q] = acc;
-    } else if (t < 2 * nline) {
-        const long long tt = t - nline;
-        const long long line = tt >> 2;  // zl*S + c
-        const int q = (int)(tt & 3);
         const long long zl = line / S, c = line % S;
         const double *p = pcol + ((size_t)zl * nchunk * S + c) * 4 + q;
-        double acc = 0.0;
-        for (int k = 0; k < nchunk; ++k) acc += p[(size_t)k * S * 4];
-        colinfo[line * 8 + q] = acc;
+        const size_t stride = (size_t)S * 4;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = 0;
+        for (; k + 3 < nchunk; k += 4) {
+            a0 += p[(size_t)k * stride];
+            a1 += p[(size_t)(k + 1) * stride];
+            a2 += p[(size_t)(k + 2) * stride];
+            a3 += p[(size_t)(k + 3) * stride];
+        }
+        for (; k < nchunk; ++k) a0 += p[(size_t)k * stride];
+        colinfo[line * 8 + q] = (a0 + a1) + (a2 + a3);
     }
 }
 

@@ -188,14 +188,37 @@ int launch_lat_dispatch(tk_plan *p, int zl_begin, int zl_end)
     return fail(TK_ERR_INVALID, "unsupported lattice kernel variant cpl=%d wc=%d", p->cpl, p->wc);
 }
 
+template <int CPL, int WC, bool K3D>
+int lat_occ_one()
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tk::lat_step_kernel<CPL, WC, K3D, 0>, 256, 0) != cudaSuccess) {
+        cudaGetLastError();
+        n = 2;
+    }
+    return std::max(n, 1);
+}
+
+// resident CTAs per SM of the step kernel variant in use
+int lat_occupancy(int cpl, int wc, bool k3d)
+{
+#define TK_CASE(CPL, WC) \
+    if (cpl == CPL && wc == WC) return k3d ? lat_occ_one<CPL, WC, true>() : lat_occ_one<CPL, WC, false>();
+    TK_CASE(1, 8) TK_CASE(1, 2) TK_CASE(1, 1)
+    TK_CASE(2, 8) TK_CASE(2, 2) TK_CASE(2, 1)
+    TK_CASE(4, 8) TK_CASE(4, 1)
+#undef TK_CASE
+    return 2;
+}
+
 int lat_finalise(tk_plan *p, const double *state, double *probe_row)
 {
-    const long long threads = 2LL * p->lat.Lloc * p->lat.S * 4;
-    const unsigned grid = (unsigned)((std::max<long long>(threads, p->n_probes) + 255) / 256);
-    tk::lat_finalise_kernel<<<grid, 256, 0, p->stream>>>(p->lat.S, p->lat.Lloc, p->nsegk, p->nchunk,
-                                                         p->prow, p->pcol, p->rowinfo, p->colinfo,
-                                                         state, p->probe_idx,
-                                                         probe_row ? p->n_probes : 0, probe_row);
+    const long long nline = (long long)p->lat.Lloc * p->lat.S;
+    const int nrowblk = (int)((nline + 7) / 8);
+    const int ncolblk = (int)((nline * 4 + 255) / 256);
+    tk::lat_finalise_kernel<<<(unsigned)(nrowblk + ncolblk), 256, 0, p->stream>>>(
+        p->lat.S, p->lat.Lloc, p->nsegk, p->nchunk, nrowblk, p->prow, p->pcol, p->rowinfo, p->colinfo,
+        state, p->probe_idx, probe_row ? p->n_probes : 0, probe_row);
     p->launches++;
     TK_CUDA(cudaGetLastError());
     return TK_OK;
@@ -521,17 +544,18 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     const int nsegk_max = (int)((S + 31) / 32);
     p->nsegk = (int)((S + 32 * p->cpl - 1) / (32 * p->cpl));
     {
-        // rows per CTA: trade the column-partial traffic (16/rchunk B per update) against wave
+        // rows per CTA: trade the per-CTA column traffic (colinfo read + pcol write = 96 B per
+        // cell per chunk, i.e. a fraction 1/rchunk of the streaming bytes) against wave
         // quantisation on (SMs x resident CTAs) slots
         const int wz = 8 / p->wc;
         const long long nct = (p->nsegk + p->wc - 1) / p->wc, nzg = (Lloc + wz - 1) / wz;
-        const long long slots = (long long)p->sm_count * 3;
+        const long long slots = (long long)p->sm_count * lat_occupancy(p->cpl, p->wc, halo != 0);
         int best = 16;
         double best_eff = -1.0;
-        for (int rc_ = 16; rc_ <= 256; rc_ *= 2) {
+        for (int rc_ = 16; rc_ <= 256 && rc_ <= std::max<long long>(16, S); ++rc_) {
             const long long tiles = ((S + rc_ - 1) / rc_) * nct * nzg;
             const long long waves = (tiles + slots - 1) / slots;
-            const double eff = (double)tiles / (double)(waves * slots) * (24.0 / (24.0 + 16.0 / rc_));
+            const double eff = (double)tiles / (double)(waves * slots) * (1.0 / (1.0 + 1.0 / rc_));
             if (eff > best_eff + 1e-9) { best_eff = eff; best = rc_; }
         }
         p->rchunk = env_int("TK_LAT_RCHUNK", best);
@@ -858,6 +882,16 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     return TK_OK;
 #undef TK_RUN_TRY
 #undef TK_RUN_CUDA
+}
+
+int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchunk, int32_t *occ)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    if (cpl) *cpl = p->cpl;
+    if (wc) *wc = p->wc;
+    if (rchunk) *rchunk = p->rchunk;
+    if (occ) *occ = lat_occupancy(p->cpl, p->wc, p->lat.halo != 0);
+    return TK_OK;
 }
 
 int tk_plan_launch_count(const tk_plan *p, int64_t *launches)

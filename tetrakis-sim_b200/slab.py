@@ -1,0 +1,280 @@
+"""Layer-slab sharding of 3-D lattices across GPUs (one process per GPU).
+
+Only the z direction of a tetrakis lattice is a true stencil: row / column cliques never leave a
+layer (reference ``tetrakis_sim/lattice.py:58-66``) and layers couple only through
+``(r,c,z,q)-(r,c,z+1,q)`` (``lattice.py:68-72``).  So rank g owns a contiguous block of layers
+plus one halo plane on each side, row/column sums stay rank-local, and a step needs exactly one
+exchange: each rank sends its first and last owned plane of u_{t+1} to its z-neighbours.  No
+all-reduce is involved (SURVEY.md sections 0.3 and 8e).
+
+Overlap: the two boundary layers are updated first, their planes go out on a side stream (NCCL
+send/recv over NVLink) while the interior layers are updated on the main stream, and the next
+step waits for the receive.  ``torch.distributed`` is plumbing only; all arithmetic is in the CUDA
+plan (``tk_lattice_step_*`` in include/tetrakis_b200.h).
+
+The orchestration is backend-agnostic (anything with the plan's phase API and four plane tensors),
+which is how tests/test_slab_gloo.py drives it on CPU with world_size 2 over gloo.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+from .lattice import LatticeSpec
+
+
+class _RawCuda:
+    """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {
+            "shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 3,
+        }  # fmt: skip
+
+
+class CudaSlabBackend:
+    """The CUDA plan of one slab + torch views of its halo planes."""
+
+    def __init__(self, spec: LatticeSpec, z_begin: int, z_end: int, device: int):
+        import torch
+
+        from .compiler import compile_lattice
+
+        self.torch = torch
+        self.device = device
+        self.plan = compile_lattice(spec, device=device, z_begin=z_begin, z_end=z_end)
+        self.plan.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        self._views: dict = {}
+
+    def planes(self, next_state: bool):
+        p = self.plan.halo_ptrs(next_state)
+        n = p["plane_bytes"] // 8
+        out = {}
+        for k in ("send_lo", "send_hi", "recv_lo", "recv_hi"):
+            key = p[k]
+            if key not in self._views:
+                self._views[key] = self.torch.as_tensor(_RawCuda(key, n), device=f"cuda:{self.device}")
+            out[k] = self._views[key]
+        return out
+
+    def __getattr__(self, name):  # step_begin / step_layers / step_end / set_state_sparse / ...
+        return getattr(self.plan, name)
+
+
+class SlabRunner:
+    """Steps one rank's slab and exchanges halos with the z-neighbours."""
+
+    def __init__(self, spec: LatticeSpec, backend, rank: int, world: int, dist=None,
+                 comm_stream=None, main_stream=None):  # fmt: skip
+        if spec.dim != 3:
+            raise ValueError("slab sharding is for 3-D lattices (2-D sheets run as replicas)")
+        if spec.layers < world:
+            raise ValueError("fewer layers than ranks")
+        self.spec, self.backend, self.rank, self.world, self.dist = spec, backend, rank, world, dist
+        self.z_begin, self.z_end = spec.slab(rank, world)
+        self.n_local_layers = self.z_end - self.z_begin
+        self.lo = rank - 1 if rank > 0 else None
+        self.hi = rank + 1 if rank < world - 1 else None
+        self.comm_stream, self.main_stream = comm_stream, main_stream
+        self._pending = []
+
+    # -- index helpers --------------------------------------------------------------------------
+    def owns(self, global_index: int) -> bool:
+        z = global_index // self.spec.plane
+        return self.z_begin <= z < self.z_end
+
+    def local_index(self, global_index: int) -> int:
+        return global_index - self.z_begin * self.spec.plane
+
+    # -- halo exchange --------------------------------------------------------------------------
+    def _post(self, next_state: bool):
+        if self.world == 1 or self.dist is None:
+            return []
+        d = self.dist
+        pl = self.backend.planes(next_state)
+        ops = []
+        # fixed global order (lower neighbour first) keeps paired sends/recvs matched
+        if self.lo is not None:
+            ops.append(d.P2POp(d.isend, pl["send_lo"], self.lo))
+            ops.append(d.P2POp(d.irecv, pl["recv_lo"], self.lo))
+        if self.hi is not None:
+            ops.append(d.P2POp(d.isend, pl["send_hi"], self.hi))
+            ops.append(d.P2POp(d.irecv, pl["recv_hi"], self.hi))
+        if not ops:
+            return []
+        if self.comm_stream is not None:
+            import torch
+
+            ev = torch.cuda.Event()
+            ev.record(self.main_stream)
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                return d.batch_isend_irecv(ops)
+        return d.batch_isend_irecv(ops)
+
+    def _wait(self):
+        for r in self._pending:
+            r.wait()  # NCCL: orders the current (main) stream after the transfer; gloo: blocks
+        self._pending = []
+
+    # -- simulation -----------------------------------------------------------------------------
+    def begin(self, coeff: float, damping: float):
+        """Row/column sums of the initial state + first halo fill."""
+        self.backend.step_begin(coeff, damping)
+        self._pending = self._post(next_state=False)
+        self._wait()
+
+    def step(self):
+        L = self.n_local_layers
+        b = self.backend
+        self._wait()  # halos of u_t are in place
+        b.step_layers(0, 1)
+        if L > 1:
+            b.step_layers(L - 1, L)
+        self._pending = self._post(next_state=True)  # boundary planes of u_{t+1} leave now ...
+        if L > 2:
+            b.step_layers(1, L - 1)  # ... while the interior is updated
+        b.step_end()
+
+    def finish(self):
+        self._wait()
+
+
+def global_max_degree(plan_max: int, dist, device=None) -> int:
+    """CFL input: max degree over all slabs (reference physics.py:64) -- a one-off scalar MAX."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return plan_max
+    import torch
+
+    t = torch.tensor([plan_max], dtype=torch.int64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): weak scaling, 64 layers of 1024x1024 per GPU (BASELINE configs[2])
+# ------------------------------------------------------------------------------------------------
+def bench_slabs(args) -> int:
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    workload = args.workload or "cfg3-slab-1024x64"
+    size = args.size or 1024
+    per_gpu = args.layers or 64
+    spec = LatticeSpec(size=size, dim=3, layers=per_gpu * world, defect="blackhole", radius=64.0)
+
+    main = torch.cuda.current_stream(dev)
+    comm = torch.cuda.Stream(dev)
+    backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=local)
+    runner = SlabRunner(spec, backend, rank, world, dist, comm_stream=comm, main_stream=main)
+    maxdeg = global_max_degree(backend.max_degree, dist, dev)
+    dt_eff = min(0.1, 1.0 / np.sqrt(maxdeg))
+    coeff = dt_eff**2
+    kick = spec.index(spec.kick_node())
+    kicks = ([runner.local_index(kick)], [1.0]) if runner.owns(kick) else ([], [])
+
+    def run(steps):
+        runner.begin(coeff, 0.0)
+        for _ in range(steps):
+            runner.step()
+        runner.finish()
+
+    from bench import ClockSampler  # same sampler as the single-GPU arm
+
+    clk = ClockSampler(local).start()
+    backend.set_state_sparse(*kicks)
+    run(args.warmup)
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0 = backend.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with clk:
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record(main)
+        runner.begin(coeff, 0.0)
+        for _ in range(args.steps):
+            runner.step()
+        runner.finish()
+        e1.record(main)
+        torch.cuda.synchronize()
+        dist.barrier()
+    launches = backend.launches - l0
+    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    n_updates = spec.num_nodes
+    value = n_updates * args.steps / (ms * 1e-3) / 1e9
+
+    # whole-lattice checksum: sum_i u_t(i) = 1 + t (unit masses; removed nodes stay 0)
+    final_t, final = None, None
+    final_t = torch.empty(backend.num_nodes, dtype=torch.float64, pin_memory=True)
+    final = final_t.numpy()
+    _lib.check(_lib.lib().tk_plan_get_state(backend.plan._h, _lib._p(final), None))
+    cs = torch.tensor([float(final.sum())], dtype=torch.float64, device=dev)
+    dist.all_reduce(cs)
+
+    # e2e: kicks H2D, K steps with halo exchange, final state D2H to pinned host memory, per rank
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    backend.set_state_sparse(*kicks)
+    run(args.steps)
+    _lib.check(_lib.lib().tk_plan_get_state(backend.plan._h, _lib._p(final), None))
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item())
+
+    # roofline of the step kernel on this rank's slab, no communication (rank 0 reports)
+    backend.set_state_sparse(*kicks)
+    o = backend.plan.run(min(args.steps, 50), coeff, 0.0, timed=True)
+    kms = o["step_kernel_ms"] / min(args.steps, 50)
+    local_nodes = backend.num_nodes  # slots; the black hole removes < 1 %
+    from bench import BYTES_PER_UPDATE, METRIC, UNIT, measured_peak_gbs
+
+    peak, peak_src = measured_peak_gbs()
+    achieved = local_nodes * BYTES_PER_UPDATE / (kms * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload,
+                       "lattice": f"3-D tetrakis {size}x{size}x{spec.layers} ({per_gpu} layers per GPU), "
+                                  f"black hole r=64 at the global centre, fp64",
+                       "nodes": n_updates, "max_degree": maxdeg, "effective_dt": dt_eff,
+                       "parallelism": f"z-slabs x{world}, 1-plane halos, NCCL send/recv overlapped "
+                                      "with interior layers",
+                       "halo_bytes_per_direction": size * size * 32,
+                       "l2": "slab state >> 126 MB L2 (no flush needed)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "lat_step_kernel (one slab, no communication)",
+                         "bytes_per_update": BYTES_PER_UPDATE, "kernel_ms_per_launch": kms},
+            "cpu_baseline": None,
+            "e2e": {"value": n_updates * args.steps / e2e_s / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": 16.0 / args.steps,
+                    "d2h_bytes_per_step": world * final.nbytes / args.steps, "seconds": e2e_s},
+            "gpu_launches": launches, "clocks": clk.summary(),
+            "checksum_sum_u": float(cs.item()), "checksum_expected": float(args.warmup + args.steps + 1),
+        }
+        print(json.dumps(line), flush=True)
+    backend.plan.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -39,6 +39,39 @@ __device__ __forceinline__ void warp_sum4_store(const double v[4], int lane, dou
     if ((lane & 7) == 0) dst[lane >> 3] = b;
 }
 
+// 256-bit global accesses (one 32-byte cell = 4 quadrant values per instruction; sm_100 LDG/STG.256).
+__device__ __forceinline__ void ld256_nc(const double *p, double v[4])  // read-only for the kernel
+{
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld256_cs(const double *p, double v[4])  // streamed once (evict-first)
+{
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256_cs(double *p, const double v[4])
+{
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+__device__ __forceinline__ void st256(double *p, const double v[4])
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+// 16-byte asynchronous global->shared copy (LDGSTS); ok == false writes zeros and reads nothing.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool ok)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(sa), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

@@ -112,6 +112,7 @@ struct tk_plan {
     tk::LatDev lat{};
     double *rowinfo = nullptr, *colinfo = nullptr, *prow = nullptr, *pcol = nullptr;
     int cpl = 2, wc = 8, rchunk = 64, nchunk = 1, nsegk = 1;
+    int wz3d = 0, stages3d = 0;  // > 0: 3-D steps use lat_step3d_kernel<wz3d, stages3d>
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
     std::vector<long long> dead_local;  // ABI-local indices of removed nodes (for dense set_state)
@@ -186,6 +187,70 @@ int launch_lat_dispatch(tk_plan *p, int zl_begin, int zl_end)
     TK_CASE(4, 8) TK_CASE(4, 1)
 #undef TK_CASE
     return fail(TK_ERR_INVALID, "unsupported lattice kernel variant cpl=%d wc=%d", p->cpl, p->wc);
+}
+
+template <int WZ, int STAGES>
+constexpr size_t lat3d_smem() { return (size_t)STAGES * (2 * WZ + 2) * 1024; }
+
+template <int WZ, int STAGES>
+int launch_lat3d(tk_plan *p, int zl_begin, int zl_end)
+{
+    static bool configured = false;
+    auto kern = tk::lat_step3d_kernel<WZ, STAGES>;
+    if (!configured) {
+        TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)lat3d_smem<WZ, STAGES>()));
+        configured = true;
+    }
+    const int nzg = (zl_end - zl_begin + WZ - 1) / WZ;
+    const long long grid = (long long)p->nchunk * p->nsegk * nzg;
+    if (grid <= 0) return TK_OK;
+    if (grid > 0x7fffffffLL) return fail(TK_ERR_INVALID, "lattice grid too large");
+    kern<<<(unsigned)grid, WZ * 32, lat3d_smem<WZ, STAGES>(), p->stream>>>(
+        p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
+        zl_end, p->rchunk, p->nchunk, p->nsegk, nzg);
+    p->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TK_OK;
+}
+
+template <int WZ, int STAGES>
+int lat3d_occ_one()
+{
+    int n = 0;
+    auto kern = tk::lat_step3d_kernel<WZ, STAGES>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lat3d_smem<WZ, STAGES>());
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, WZ * 32, lat3d_smem<WZ, STAGES>()) != cudaSuccess) {
+        cudaGetLastError();
+        n = 1;
+    }
+    return std::max(n, 1);
+}
+
+#define TK_3D_VARIANTS(X) X(4, 4) X(8, 3) X(8, 4) X(8, 6) X(16, 3) X(16, 4)
+
+bool lat3d_supported(int wz, int st)
+{
+#define X(WZ, ST) if (wz == WZ && st == ST) return true;
+    TK_3D_VARIANTS(X)
+#undef X
+    return false;
+}
+
+int lat3d_occupancy(int wz, int st)
+{
+#define X(WZ, ST) if (wz == WZ && st == ST) return lat3d_occ_one<WZ, ST>();
+    TK_3D_VARIANTS(X)
+#undef X
+    return 1;
+}
+
+int launch_lat3d_dispatch(tk_plan *p, int zl_begin, int zl_end)
+{
+#define X(WZ, ST) if (p->wz3d == WZ && p->stages3d == ST) return launch_lat3d<WZ, ST>(p, zl_begin, zl_end);
+    TK_3D_VARIANTS(X)
+#undef X
+    return fail(TK_ERR_INVALID, "unsupported 3-D kernel variant wz=%d stages=%d", p->wz3d, p->stages3d);
 }
 
 template <int CPL, int WC, bool K3D>
@@ -541,15 +606,25 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     p->cpl = env_int("TK_LAT_CPL", 1);
     p->wc = env_int("TK_LAT_WC", halo ? 1 : 8);
     if (p->cpl != 1 && p->cpl != 2 && p->cpl != 4) p->cpl = 2;
+    if (halo && env_int("TK_LAT3D", 1)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
+        p->wz3d = env_int("TK_LAT3D_WZ", 8);
+        p->stages3d = env_int("TK_LAT3D_STAGES", 4);
+        if (!lat3d_supported(p->wz3d, p->stages3d)) { p->wz3d = 8; p->stages3d = 4; }
+        p->cpl = 1;
+        p->wc = 1;
+    }
     const int nsegk_max = (int)((S + 31) / 32);
     p->nsegk = (int)((S + 32 * p->cpl - 1) / (32 * p->cpl));
     {
         // rows per CTA: trade the per-CTA column traffic (colinfo read + pcol write = 96 B per
         // cell per chunk, i.e. a fraction 1/rchunk of the streaming bytes) against wave
         // quantisation on (SMs x resident CTAs) slots
-        const int wz = 8 / p->wc;
-        const long long nct = (p->nsegk + p->wc - 1) / p->wc, nzg = (Lloc + wz - 1) / wz;
-        const long long slots = (long long)p->sm_count * lat_occupancy(p->cpl, p->wc, halo != 0);
+        const int wz = p->wz3d ? p->wz3d : 8 / p->wc;
+        const long long nct = p->wz3d ? p->nsegk : (p->nsegk + p->wc - 1) / p->wc;
+        const long long nzg = (Lloc + wz - 1) / wz;
+        const long long slots =
+            (long long)p->sm_count * (p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d)
+                                              : lat_occupancy(p->cpl, p->wc, halo != 0));
         int best = 16;
         double best_eff = -1.0;
         for (int rc_ = 16; rc_ <= 256 && rc_ <= std::max<long long>(16, S); ++rc_) {
@@ -752,6 +827,7 @@ int tk_lattice_step_layers(tk_plan *p, int32_t zl_begin, int32_t zl_end)
 {
     TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
     TK_REQUIRE(0 <= zl_begin && zl_begin <= zl_end && zl_end <= p->lat.Lloc, "bad layer range");
+    if (p->wz3d) return launch_lat3d_dispatch(p, zl_begin, zl_end);
     return launch_lat_dispatch<0>(p, zl_begin, zl_end);
 }
 
@@ -844,7 +920,7 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
         for (int64_t s = 0; s < a->steps; ++s) {
             const bool tk_ = (size_t)(2 * s + 1) < kev.size();
             if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s], p->stream));
-            TK_RUN_TRY(launch_lat_dispatch<0>(p, 0, p->lat.Lloc));
+            TK_RUN_TRY(tk_lattice_step_layers(p, 0, p->lat.Lloc));
             if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s + 1], p->stream));
             TK_RUN_TRY(tk_lattice_step_end(p));
             TK_RUN_CUDA(record());
@@ -888,9 +964,10 @@ int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchu
 {
     TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
     if (cpl) *cpl = p->cpl;
-    if (wc) *wc = p->wc;
+    if (wc) *wc = p->wz3d ? -p->wz3d * 100 - p->stages3d : p->wc;  // 3-D: -(100*layers_per_cta + stages)
     if (rchunk) *rchunk = p->rchunk;
-    if (occ) *occ = lat_occupancy(p->cpl, p->wc, p->lat.halo != 0);
+    if (occ) *occ = p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d)
+                            : lat_occupancy(p->cpl, p->wc, p->lat.halo != 0);
     return TK_OK;
 }
 

@@ -89,9 +89,26 @@ VARIANTS = [(1, 8, 16), (1, 2, 32), (1, 1, 64), (2, 8, 16), (2, 2, 32), (2, 1, 2
 @pytest.mark.parametrize("case", ["2d_hole", "3d_sing", "3d_wedge_odd"])
 def test_every_kernel_variant_against_the_oracle(cpl, wc, rchunk, case, monkeypatch):
     """Medium lattices (several segments, ragged tails, many row chunks) vs the C oracle."""
+    monkeypatch.setenv("TK_LAT3D", "0")  # the register-path kernel, also for the 3-D cases
+    _variant_case(cpl, wc, rchunk, case, monkeypatch)
+
+
+@pytest.mark.parametrize("wz,stages,rchunk", [(8, 4, 0), (8, 3, 16), (8, 6, 40), (4, 4, 7), (16, 3, 64),
+                                              (16, 4, 5)])
+@pytest.mark.parametrize("case", ["3d_sing", "3d_wedge_odd", "3d_hole_tall"])
+def test_3d_staged_kernel_variants_against_the_oracle(wz, stages, rchunk, case, monkeypatch):
+    """lat_step3d_kernel (cp.async-staged z neighbours): partial z-groups, ragged segments, short
+    and long row chunks (fewer rows than pipeline stages included)."""
+    monkeypatch.setenv("TK_LAT3D_WZ", str(wz))
+    monkeypatch.setenv("TK_LAT3D_STAGES", str(stages))
+    _variant_case(1, 1, rchunk, case, monkeypatch)
+
+
+def _variant_case(cpl, wc, rchunk, case, monkeypatch):
     monkeypatch.setenv("TK_LAT_CPL", str(cpl))
     monkeypatch.setenv("TK_LAT_WC", str(wc))
-    monkeypatch.setenv("TK_LAT_RCHUNK", str(rchunk))
+    if rchunk:
+        monkeypatch.setenv("TK_LAT_RCHUNK", str(rchunk))
     if case == "2d_hole":
         spec = tk.LatticeSpec(size=150, dim=2, defect="blackhole", radius=9.3, center=(70, 66))
         steps, damping = 30, 0.01
@@ -99,6 +116,9 @@ def test_every_kernel_variant_against_the_oracle(cpl, wc, rchunk, case, monkeypa
         spec = tk.LatticeSpec(size=70, dim=3, layers=11, defect="singularity", radius=3.0,
                               mass=2000.0, potential=1.5, prune_edges=True)
         steps, damping = 20, 0.0
+    elif case == "3d_hole_tall":
+        spec = tk.LatticeSpec(size=45, dim=3, layers=21, defect="blackhole", radius=5.2)
+        steps, damping = 12, 0.0
     else:
         spec = tk.LatticeSpec(size=37, dim=3, layers=9, defect="wedge")
         steps, damping = 25, 0.02

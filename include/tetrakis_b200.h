@@ -158,6 +158,43 @@ int tk_lattice_tiling(const tk_plan *plan, int32_t *cells_per_lane, int32_t *seg
 int tk_dft_abs(int device, const double *series, int64_t batch, int64_t n, double *spectrum,
                int64_t *argmax);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched ensembles: n_sims independent simulations of ONE small lattice shape, each with its own
+ * defect mask, kick node, coeff = (c*dt_eff)^2 and damping; one simulation per CTA, state resident
+ * in shared memory.  Replaces one Python process per parameter point
+ * (examples/naked_singularity_sweep.py:211-212) and the serial loop of evals/dataset.py:81-163.
+ *   cell_bits  [n_masks][layers*size*size]  bits 0-3 part(q), bits 4-7 alive(q)
+ *   exc_*      tagged nodes of each mask (CSR over masks): node index, inv_mass, potential
+ *   corr_*     directed edge corrections of each mask (CSR over masks, <= 32 per mask)
+ *   sim_*      per simulation: mask id, kicked (= probed) node, kick value, coeff, damping
+ * Outputs (host): probe series [n_sims][steps+1]; |DFT| of it [n_sims][steps+1] (or NULL);
+ * np.argmax of the spectrum [n_sims] (or NULL); device time of the kernel in ms (or NULL).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct tk_ensemble_desc {
+    int32_t size;
+    int32_t layers;
+    int64_t n_masks;
+    const uint8_t *cell_bits;
+    const int32_t *exc_offset; /* [n_masks+1] or NULL */
+    const int32_t *exc_node;
+    const double *exc_inv_mass;
+    const double *exc_potential;
+    const int32_t *corr_offset; /* [n_masks+1] or NULL */
+    const int32_t *corr_a;
+    const int32_t *corr_b;
+    const double *corr_sign;
+    int64_t n_sims;
+    const int32_t *sim_mask;
+    const int32_t *sim_kick;
+    const double *sim_kick_value; /* NULL = 1.0 */
+    const double *sim_coeff;
+    const double *sim_damping;
+    int64_t steps;
+} tk_ensemble_desc;
+
+int tk_ensemble_run(int device, const tk_ensemble_desc *desc, double *probe_series,
+                    double *spectrum, int64_t *argmax, double *elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,3 +164,22 @@ def test_install_rebinds_reference_entry_points():
         assert fake.run_wave_sim is not tk.run_wave_sim
     finally:
         del sys.modules["tetrakis_sim.physics"], sys.modules["user_script"]
+
+
+@pytest.mark.parametrize("name", lattice_names())
+def test_ensemble_mask_arrays_match_the_reference_graph(name):
+    from tetrakis_sim_b200.ensemble import mask_arrays
+
+    g = load_golden(name)
+    spec = _spec_from(g["lattice"])
+    bits, exc, corr, max_degree, n_alive = mask_arrays(spec)
+    assert max_degree == g["metadata"]["max_degree"]
+    assert n_alive == len(g["nodes"]) and bits.shape == (spec.num_slots // 4,)
+    tagged = np.flatnonzero((g["inv_mass"] != 1.0) | (g["potential"] != 0.0))
+    assert len(exc[0]) == len(tagged)
+
+
+def test_sweep_grid_ordering():
+    specs, damp, dt = tk.sweep_grid(13, 7, [0.5, 4.0], [0.0, 0.05, 0.1], [0.02, 0.2])
+    assert len(specs) == 12 and specs[0] is specs[5] and specs[6].radius == 4.0
+    assert damp.tolist() == [0.0, 0.0, 0.05, 0.05, 0.1, 0.1] * 2 and dt.tolist() == [0.02, 0.2] * 6

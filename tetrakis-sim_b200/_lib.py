@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
     "tk_plan_run", "tk_plan_launch_count", "tk_plan_destroy",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
-    "tk_lattice_step_end", "tk_lattice_tiling", "tk_dft_abs",
+    "tk_lattice_step_end", "tk_lattice_tiling", "tk_dft_abs", "tk_ensemble_run",
 )  # fmt: skip
 
 
@@ -56,6 +56,17 @@ class RunArgs(ctypes.Structure):
         ("n_probes", c_int64), ("probe_index", c_void_p), ("probe_out", c_void_p),
         ("history_out", c_void_p), ("energy_out", c_void_p), ("elapsed_ms", c_void_p),
         ("step_kernel_ms", c_void_p),
+    ]  # fmt: skip
+
+
+class EnsembleDesc(ctypes.Structure):
+    _fields_ = [
+        ("size", c_int32), ("layers", c_int32), ("n_masks", c_int64), ("cell_bits", c_void_p),
+        ("exc_offset", c_void_p), ("exc_node", c_void_p), ("exc_inv_mass", c_void_p),
+        ("exc_potential", c_void_p), ("corr_offset", c_void_p), ("corr_a", c_void_p),
+        ("corr_b", c_void_p), ("corr_sign", c_void_p), ("n_sims", c_int64), ("sim_mask", c_void_p),
+        ("sim_kick", c_void_p), ("sim_kick_value", c_void_p), ("sim_coeff", c_void_p),
+        ("sim_damping", c_void_p), ("steps", c_int64),
     ]  # fmt: skip
 
 
@@ -100,6 +111,7 @@ def lib():
     L.tk_lattice_tiling.argtypes = [P, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                                     POINTER(c_int32)]  # fmt: skip
     L.tk_dft_abs.argtypes = [c_int, P, c_int64, c_int64, P, P]
+    L.tk_ensemble_run.argtypes = [c_int, POINTER(EnsembleDesc), P, P, P, POINTER(c_double)]
     for name in ABI_SYMBOLS:
         fn = getattr(L, name)
         if name not in ("tk_last_error",):

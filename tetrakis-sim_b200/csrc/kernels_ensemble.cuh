@@ -1,0 +1,202 @@
+// Batched ensembles: one independent small-lattice simulation per CTA, state resident in shared
+// memory for all its steps (no HBM state traffic), probe DFT fused into the epilogue.
+//
+// Replaces one Python process per parameter point (reference examples/naked_singularity_sweep.py:
+// 211-212) and the serial loop of tetrakis_sim/evals/dataset.py:81-163; each simulation is the same
+// leapfrog update as reference tetrakis_sim/physics.py:104-129 on a lattice.py sheet with a
+// defects.py mask, evaluated with the clique-sum form (see kernels_lattice.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace tk {
+
+struct EnsDev {
+    int S, L;          // cells per side, layers
+    int n_masks;
+    int steps;
+    const unsigned char *cell_bits;  // [n_masks][L*S*S] bits 0-3 part(q), 4-7 alive(q)
+    const double *attr_im;           // [n_attr_rows][N] dense inv_mass rows for masks that carry tags
+    const double *attr_v;            // [n_attr_rows][N] potential
+    const int *mask_attr_row;        // [n_masks] row of attr_* or -1
+    const int *corr_off;             // [n_masks+1]
+    const int *corr_a, *corr_b;      // node indices
+    const double *corr_sign;
+    const int *sim_mask, *sim_kick;  // [n_sims]
+    const double *sim_coeff, *sim_damping, *sim_kick_value;
+    double *series;    // [n_sims][steps+1]
+    double *spectrum;  // [n_sims][steps+1] or nullptr
+    long long *argmax; // [n_sims] or nullptr
+};
+
+constexpr int kEnsMaxCorr = 32;
+
+__global__ void __launch_bounds__(448, 2)
+ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
+{
+    extern __shared__ __align__(16) unsigned char tk_smem[];
+    const int S = P.S, L = P.L, ncell = L * S * S, N = ncell * 4, nline = L * S * 4;
+    const int nt = P.steps + 1;
+    double *ua = reinterpret_cast<double *>(tk_smem);
+    double *ub = ua + N;
+    double *rs = ub + N;        // [L][S][4] row sums
+    double *cs = rs + nline;    // [L][S][4] column sums
+    double *series = cs + nline;  // [nt]
+    double *twc = series + nt;    // [nt] cos(2 pi j / nt)
+    double *tws = twc + nt;       // [nt] sin(2 pi j / nt)
+    double *csig = tws + nt;      // [kEnsMaxCorr]
+    float *rc = reinterpret_cast<float *>(csig + kEnsMaxCorr);  // [nline] row participation counts
+    float *cc = rc + nline;                                     // [nline]
+    int *ca = reinterpret_cast<int *>(cc + nline);              // [kEnsMaxCorr]
+    int *cb = ca + kEnsMaxCorr;
+    unsigned char *bits = reinterpret_cast<unsigned char *>(cb + kEnsMaxCorr);  // [ncell]
+
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int j = tid; j < nt; j += nth) {
+        double s, c;
+        sincospi(2.0 * (double)j / (double)nt, &s, &c);
+        twc[j] = c;
+        tws[j] = s;
+    }
+
+    for (long long sim = blockIdx.x; sim < n_sims; sim += gridDim.x) {
+        const int mask = P.sim_mask[sim];
+        const int kick = P.sim_kick[sim];
+        const double coeff = P.sim_coeff[sim], damping = P.sim_damping[sim];
+        const unsigned char *gbits = P.cell_bits + (size_t)mask * ncell;
+        const int arow = P.mask_attr_row[mask];
+        const bool has_attr = arow >= 0;
+        const double *gim = P.attr_im + (size_t)(has_attr ? arow : 0) * N;
+        const double *gv = P.attr_v + (size_t)(has_attr ? arow : 0) * N;
+        const int c0 = P.corr_off[mask];
+        const int ncorr = min(P.corr_off[mask + 1] - c0, kEnsMaxCorr);
+
+        __syncthreads();  // previous simulation fully drained
+        for (int i = tid; i < N; i += nth) { ua[i] = 0.0; ub[i] = 0.0; }
+        for (int i = tid; i < ncell; i += nth) bits[i] = gbits[i];
+        for (int i = tid; i < nt; i += nth) series[i] = 0.0;
+        for (int i = tid; i < ncorr; i += nth) {
+            ca[i] = P.corr_a[c0 + i];
+            cb[i] = P.corr_b[c0 + i];
+            csig[i] = P.corr_sign[c0 + i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ua[kick] = P.sim_kick_value[sim];
+            series[0] = ua[kick];
+        }
+        // static participation counts of every row / column line
+        for (int i = tid; i < 2 * nline; i += nth) {
+            const bool is_col = i >= nline;
+            const int l = is_col ? i - nline : i;
+            const int q = l & 3, x = (l >> 2) % S, z = (l >> 2) / S;
+            int cnt = 0;
+            for (int k = 0; k < S; ++k) {
+                const int cell = is_col ? (z * S + k) * S + x : (z * S + x) * S + k;
+                cnt += (bits[cell] >> q) & 1;
+            }
+            (is_col ? cc : rc)[l] = (float)cnt;
+        }
+        double *u = ua, *w = ub;
+        for (int t = 0; t < P.steps; ++t) {
+            __syncthreads();
+            // phase A: masked row / column sums of u_t
+            for (int i = tid; i < 2 * nline; i += nth) {
+                const bool is_col = i >= nline;
+                const int l = is_col ? i - nline : i;
+                const int q = l & 3, x = (l >> 2) % S, z = (l >> 2) / S;
+                double acc = 0.0;
+                for (int k = 0; k < S; ++k) {
+                    const int cell = is_col ? (z * S + k) * S + x : (z * S + x) * S + k;
+                    if ((bits[cell] >> q) & 1) acc += u[cell * 4 + q];
+                }
+                (is_col ? cs : rs)[l] = acc;
+            }
+            __syncthreads();
+            // phase B: update every cell; u_{t+1} overwrites u_{t-1}
+            for (int cell = tid; cell < ncell; cell += nth) {
+                const int c = cell % S, r = (cell / S) % S, z = cell / (S * S);
+                const unsigned f = bits[cell];
+                const unsigned fm = z > 0 ? bits[cell - S * S] : 0u;
+                const unsigned fp = z < L - 1 ? bits[cell + S * S] : 0u;
+                const double2 a = *reinterpret_cast<const double2 *>(u + cell * 4);
+                const double2 b = *reinterpret_cast<const double2 *>(u + cell * 4 + 2);
+                const double uq[4] = {a.x, a.y, b.x, b.y};
+                double cellsum = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if ((f >> q) & 1u) cellsum += uq[q];
+                const double ccnt = (double)__popc(f & 0xFu);
+                double un[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int node = cell * 4 + q;
+                    const bool part = (f >> q) & 1u, alive = (f >> (4 + q)) & 1u;
+                    double lap = 0.0;
+                    if (part) {
+                        double nsum = (cellsum - uq[q]) + (rs[(z * S + r) * 4 + q] - uq[q]) +
+                                      (cs[(z * S + c) * 4 + q] - uq[q]);
+                        double deg = (ccnt - 1.0) + ((double)rc[(z * S + r) * 4 + q] - 1.0) +
+                                     ((double)cc[(z * S + c) * 4 + q] - 1.0);
+                        if ((fm >> q) & 1u) { nsum += u[node - S * S * 4]; deg += 1.0; }
+                        if ((fp >> q) & 1u) { nsum += u[node + S * S * 4]; deg += 1.0; }
+                        lap = nsum - deg * uq[q];
+                    }
+                    for (int k = 0; k < ncorr; ++k)
+                        if (ca[k] == node) lap += csig[k] * (u[cb[k]] - uq[q]);
+                    double im = 1.0, v = 0.0;
+                    if (has_attr) { im = gim[node]; v = gv[node]; }
+                    const double up = w[node];
+                    const double rnew = 2.0 * uq[q] - up + (coeff * im) * lap - (coeff * v) * uq[q] -
+                                        damping * (uq[q] - up);
+                    un[q] = alive ? rnew : 0.0;
+                    if (node == kick) series[t + 1] = un[q];
+                }
+                *reinterpret_cast<double2 *>(w + cell * 4) = make_double2(un[0], un[1]);
+                *reinterpret_cast<double2 *>(w + cell * 4 + 2) = make_double2(un[2], un[3]);
+            }
+            double *tmp = u; u = w; w = tmp;
+        }
+        __syncthreads();
+        // epilogue: probe series out, |DFT| (reference physics.py:162-163) and argmax (batch.py:205)
+        for (int j = tid; j < nt; j += nth) P.series[(size_t)sim * nt + j] = series[j];
+        if (P.spectrum) {
+            double *spec = rs;  // row sums are dead now; reuse if large enough, else recompute below
+            const bool fits = nt <= 2 * nline;
+            for (int k = tid; k < nt; k += nth) {
+                double re = 0.0, imag = 0.0;
+                int m = 0;  // (k*j) mod nt, updated incrementally
+                for (int j = 0; j < nt; ++j) {
+                    re += series[j] * twc[m];
+                    imag -= series[j] * tws[m];
+                    m += k;
+                    if (m >= nt) m -= nt;
+                }
+                const double mag = hypot(re, imag);
+                P.spectrum[(size_t)sim * nt + k] = mag;
+                if (fits) spec[k] = mag;
+            }
+            if (P.argmax) {
+                __syncthreads();
+                if (tid == 0) {
+                    double best = -1.0;
+                    int bi = 0;
+                    for (int k = 0; k < nt; ++k) {
+                        const double mag = fits ? spec[k] : P.spectrum[(size_t)sim * nt + k];
+                        if (mag > best) { best = mag; bi = k; }
+                    }
+                    P.argmax[sim] = bi;
+                }
+            }
+        }
+    }
+}
+
+inline size_t ensemble_smem_bytes(int S, int L, int steps)
+{
+    const size_t ncell = (size_t)L * S * S, N = ncell * 4, nline = (size_t)L * S * 4, nt = steps + 1;
+    size_t b = (2 * N + 2 * nline + 3 * nt + kEnsMaxCorr) * sizeof(double);
+    b += 2 * nline * sizeof(float) + 2 * kEnsMaxCorr * sizeof(int) + ncell;
+    return (b + 15) & ~(size_t)15;
+}
+
+}  // namespace tk

@@ -101,8 +101,8 @@ __device__ __noinline__ void cell_update_detail(const LatDev &P, const double *_
 }
 
 // MODE 0: leapfrog step.  MODE 1: sums only (row/col sums of the current state, no update).
-template <int CPL, int WC, bool K3D, int MODE>
-__global__ void __launch_bounds__(256)
+template <int CPL, int WC, bool K3D, int MODE, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
 lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
                 double *__restrict__ w, double *__restrict__ prow, double *__restrict__ pcol,
                 double coeff, double damping, int zl_begin, int zl_end, int rchunk, int nchunk,
@@ -252,8 +252,8 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
 // for WZ = 8), and HBM traffic stays ~24 B because the two halo rows are the rows the neighbouring
 // z-group CTA streams at the same time (z-groups are the fastest block index).
 // Slots of layers that do not exist are zero-filled (src-size 0), matching deg via degbase/flags.
-template <int WZ, int STAGES>
-__global__ void __launch_bounds__(WZ * 32)
+template <int WZ, int STAGES, int MINB>
+__global__ void __launch_bounds__(WZ * 32, MINB)
 lat_step3d_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
                   double *__restrict__ w, double *__restrict__ prow, double *__restrict__ pcol,
                   double coeff, double damping, int zl_begin, int zl_end, int rchunk, int nchunk,
@@ -261,8 +261,13 @@ lat_step3d_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u
 {
     extern __shared__ __align__(16) unsigned char tk_smem[];
     // sU[stage][slot 0..WZ+1][half][lane], sW[stage][wz][half][lane]   (double2 = 16 B each)
+    // sR[stage][wz][4] = the row's {RowSum(4), rowcnt(4)}, sF[stage][wz] = its defect-table entry: the
+    // small per-row loads are staged too, otherwise they queue behind the bulk prefetch traffic in the
+    // in-order L1 pipeline and every row pays a full loaded-memory latency after the barrier.
     double2 *sU = reinterpret_cast<double2 *>(tk_smem);
     double2 *sW = sU + STAGES * (WZ + 2) * 64;
+    double2 *sR = sW + STAGES * WZ * 64;
+    int *sF = reinterpret_cast<int *>(sR + STAGES * WZ * 4);
 
     const int lane = threadIdx.x & 31, wz = threadIdx.x >> 5;
     int b = blockIdx.x;
@@ -301,6 +306,10 @@ lat_step3d_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u
             cp_async16(du + 32, valid ? gu + 2 : u, valid);
             cp_async16(dw, valid ? gw : u, valid);
             cp_async16(dw + 32, valid ? gw + 2 : u, valid);
+            if (lane < 4)
+                cp_async16(sR + (s * WZ + wz) * 4 + lane, P.rowinfo + ((size_t)zl * S + r) * 8 + lane * 2, true);
+            if (lane == 4)
+                cp_async4(sF + s * WZ + wz, P.seg_flag + ((size_t)zl * S + r) * P.ntab + (segk * 32) / kTabSeg);
             if (wz == 0) {  // halo row below the CTA's first layer
                 const bool ok = valid && zm_on;
                 double2 *dh = sU + ((s * (WZ + 2)) * 2) * 32 + lane;
@@ -348,12 +357,15 @@ lat_step3d_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u
                 const double2 w0 = pw[0], w1 = pw[32];
                 upq[0] = w0.x; upq[1] = w0.y; upq[2] = w1.x; upq[3] = w1.y;
             }
-            int det = -1;
-            if (valid) det = P.seg_flag[((size_t)zl * S + r) * P.ntab + c / kTabSeg];
-            const bool all_plain = __all_sync(0xffffffffu, det < 0);
+            const int det = valid ? sF[s * WZ + wz] : -1;
+            const bool all_plain = sF[s * WZ + wz] < 0;  // warp-uniform (one table entry per 64 cells)
             double RS[4], RC[4];
-            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8, RS);
-            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8 + 4, RC);
+            {
+                const double2 *pr = sR + (s * WZ + wz) * 4;
+                const double2 r0 = pr[0], r1 = pr[1], r2 = pr[2], r3 = pr[3];
+                RS[0] = r0.x; RS[1] = r0.y; RS[2] = r1.x; RS[3] = r1.y;
+                RC[0] = r2.x; RC[1] = r2.y; RC[2] = r3.x; RC[3] = r3.y;
+            }
             double un[4], pun[4];
             if (all_plain) {
                 const double cell = (uq[0] + uq[1]) + (uq[2] + uq[3]);

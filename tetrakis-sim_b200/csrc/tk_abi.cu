@@ -8,9 +8,11 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
+#include "kernels_ensemble.cuh"
 #include "kernels_graph.cuh"
 #include "kernels_lattice.cuh"
 
@@ -112,7 +114,8 @@ struct tk_plan {
     tk::LatDev lat{};
     double *rowinfo = nullptr, *colinfo = nullptr, *prow = nullptr, *pcol = nullptr;
     int cpl = 2, wc = 8, rchunk = 64, nchunk = 1, nsegk = 1;
-    int wz3d = 0, stages3d = 0;  // > 0: 3-D steps use lat_step3d_kernel<wz3d, stages3d>
+    int wz3d = 0, stages3d = 0, minb3d = 2;  // wz3d > 0: 3-D steps use lat_step3d_kernel<wz3d, stages3d, minb3d>
+    int minb = 1;                            // register path: min resident CTAs per SM asked of ptxas
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
     std::vector<long long> dead_local;  // ABI-local indices of removed nodes (for dense set_state)
@@ -156,7 +159,7 @@ int env_int(const char *name, int dflt)
 }
 
 // ------------------------------------------------------------------ lattice launches
-template <int CPL, int WC, bool K3D, int MODE>
+template <int CPL, int WC, bool K3D, int MODE, int MINB = 1>
 int launch_lat(tk_plan *p, int zl_begin, int zl_end)
 {
     constexpr int WZ = 8 / WC;
@@ -166,7 +169,7 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
     const long long grid = (long long)p->nchunk * nct * nzg;
     if (grid <= 0) return TK_OK;
     if (grid > 0x7fffffffLL) return fail(TK_ERR_INVALID, "lattice grid too large");
-    tk::lat_step_kernel<CPL, WC, K3D, MODE><<<(unsigned)grid, 256, 0, p->stream>>>(
+    tk::lat_step_kernel<CPL, WC, K3D, MODE, MINB><<<(unsigned)grid, 256, 0, p->stream>>>(
         p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
         zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg);
     p->launches++;
@@ -178,6 +181,11 @@ template <int MODE>
 int launch_lat_dispatch(tk_plan *p, int zl_begin, int zl_end)
 {
     const bool k3d = p->lat.halo != 0;
+    if (MODE == 0 && k3d && p->cpl == 1 && p->minb == 3) {  // register path squeezed to 3 CTAs/SM
+        if (p->wc == 1) return launch_lat<1, 1, true, 0, 3>(p, zl_begin, zl_end);
+        if (p->wc == 2) return launch_lat<1, 2, true, 0, 3>(p, zl_begin, zl_end);
+        if (p->wc == 8) return launch_lat<1, 8, true, 0, 3>(p, zl_begin, zl_end);
+    }
 #define TK_CASE(CPL, WC)                                                         \
     if (p->cpl == CPL && p->wc == WC)                                            \
         return k3d ? launch_lat<CPL, WC, true, MODE>(p, zl_begin, zl_end)        \
@@ -190,13 +198,16 @@ int launch_lat_dispatch(tk_plan *p, int zl_begin, int zl_end)
 }
 
 template <int WZ, int STAGES>
-constexpr size_t lat3d_smem() { return (size_t)STAGES * (2 * WZ + 2) * 1024; }
+constexpr size_t lat3d_smem()
+{
+    return (size_t)STAGES * ((2 * WZ + 2) * 1024 + WZ * 64 + ((WZ * 4 + 15) / 16) * 16);
+}
 
-template <int WZ, int STAGES>
+template <int WZ, int STAGES, int MINB>
 int launch_lat3d(tk_plan *p, int zl_begin, int zl_end)
 {
     static bool configured = false;
-    auto kern = tk::lat_step3d_kernel<WZ, STAGES>;
+    auto kern = tk::lat_step3d_kernel<WZ, STAGES, MINB>;
     if (!configured) {
         TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)lat3d_smem<WZ, STAGES>()));
@@ -214,11 +225,11 @@ int launch_lat3d(tk_plan *p, int zl_begin, int zl_end)
     return TK_OK;
 }
 
-template <int WZ, int STAGES>
+template <int WZ, int STAGES, int MINB>
 int lat3d_occ_one()
 {
     int n = 0;
-    auto kern = tk::lat_step3d_kernel<WZ, STAGES>;
+    auto kern = tk::lat_step3d_kernel<WZ, STAGES, MINB>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lat3d_smem<WZ, STAGES>());
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, WZ * 32, lat3d_smem<WZ, STAGES>()) != cudaSuccess) {
         cudaGetLastError();
@@ -227,19 +238,20 @@ int lat3d_occ_one()
     return std::max(n, 1);
 }
 
-#define TK_3D_VARIANTS(X) X(4, 4) X(8, 3) X(8, 4) X(8, 6) X(16, 3) X(16, 4)
+// (layers per CTA, pipeline stages, min resident CTAs per SM)
+#define TK_3D_VARIANTS(X) X(4, 4, 4) X(8, 3, 2) X(8, 3, 3) X(8, 4, 2) X(8, 4, 3) X(8, 6, 2) X(16, 3, 1) X(16, 4, 1)
 
-bool lat3d_supported(int wz, int st)
+bool lat3d_supported(int wz, int st, int mb)
 {
-#define X(WZ, ST) if (wz == WZ && st == ST) return true;
+#define X(WZ, ST, MB) if (wz == WZ && st == ST && mb == MB) return true;
     TK_3D_VARIANTS(X)
 #undef X
     return false;
 }
 
-int lat3d_occupancy(int wz, int st)
+int lat3d_occupancy(int wz, int st, int mb)
 {
-#define X(WZ, ST) if (wz == WZ && st == ST) return lat3d_occ_one<WZ, ST>();
+#define X(WZ, ST, MB) if (wz == WZ && st == ST && mb == MB) return lat3d_occ_one<WZ, ST, MB>();
     TK_3D_VARIANTS(X)
 #undef X
     return 1;
@@ -247,10 +259,12 @@ int lat3d_occupancy(int wz, int st)
 
 int launch_lat3d_dispatch(tk_plan *p, int zl_begin, int zl_end)
 {
-#define X(WZ, ST) if (p->wz3d == WZ && p->stages3d == ST) return launch_lat3d<WZ, ST>(p, zl_begin, zl_end);
+#define X(WZ, ST, MB) \
+    if (p->wz3d == WZ && p->stages3d == ST && p->minb3d == MB) return launch_lat3d<WZ, ST, MB>(p, zl_begin, zl_end);
     TK_3D_VARIANTS(X)
 #undef X
-    return fail(TK_ERR_INVALID, "unsupported 3-D kernel variant wz=%d stages=%d", p->wz3d, p->stages3d);
+    return fail(TK_ERR_INVALID, "unsupported 3-D kernel variant wz=%d stages=%d minb=%d", p->wz3d,
+                p->stages3d, p->minb3d);
 }
 
 template <int CPL, int WC, bool K3D>
@@ -606,10 +620,12 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     p->cpl = env_int("TK_LAT_CPL", 1);
     p->wc = env_int("TK_LAT_WC", halo ? 1 : 8);
     if (p->cpl != 1 && p->cpl != 2 && p->cpl != 4) p->cpl = 2;
+    p->minb = env_int("TK_LAT_MINB", 1);
     if (halo && env_int("TK_LAT3D", 1)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
         p->wz3d = env_int("TK_LAT3D_WZ", 8);
         p->stages3d = env_int("TK_LAT3D_STAGES", 4);
-        if (!lat3d_supported(p->wz3d, p->stages3d)) { p->wz3d = 8; p->stages3d = 4; }
+        p->minb3d = env_int("TK_LAT3D_MINB", p->wz3d == 16 ? 1 : (p->wz3d == 4 ? 4 : 2));
+        if (!lat3d_supported(p->wz3d, p->stages3d, p->minb3d)) { p->wz3d = 8; p->stages3d = 4; p->minb3d = 2; }
         p->cpl = 1;
         p->wc = 1;
     }
@@ -623,7 +639,7 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
         const long long nct = p->wz3d ? p->nsegk : (p->nsegk + p->wc - 1) / p->wc;
         const long long nzg = (Lloc + wz - 1) / wz;
         const long long slots =
-            (long long)p->sm_count * (p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d)
+            (long long)p->sm_count * (p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d, p->minb3d)
                                               : lat_occupancy(p->cpl, p->wc, halo != 0));
         int best = 16;
         double best_eff = -1.0;
@@ -966,7 +982,7 @@ int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchu
     if (cpl) *cpl = p->cpl;
     if (wc) *wc = p->wz3d ? -p->wz3d * 100 - p->stages3d : p->wc;  // 3-D: -(100*layers_per_cta + stages)
     if (rchunk) *rchunk = p->rchunk;
-    if (occ) *occ = p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d)
+    if (occ) *occ = p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d, p->minb3d)
                             : lat_occupancy(p->cpl, p->wc, p->lat.halo != 0);
     return TK_OK;
 }
@@ -1021,6 +1037,133 @@ int tk_dft_abs(int device, const double *series, int64_t batch, int64_t n, doubl
     cudaFree(d_a);
     TK_CUDA(e);
     return TK_OK;
+}
+
+// ------------------------------------------------------------------------------ ensembles
+int tk_ensemble_run(int device, const tk_ensemble_desc *d, double *probe_series, double *spectrum,
+                    int64_t *argmax, double *elapsed_ms)
+{
+    TK_REQUIRE(d && probe_series, "NULL argument");
+    TK_REQUIRE(d->size >= 1 && d->layers >= 1 && d->n_masks >= 1 && d->n_sims >= 0 && d->steps >= 0,
+               "bad ensemble shape");
+    TK_REQUIRE(d->cell_bits && (d->n_sims == 0 || (d->sim_mask && d->sim_kick && d->sim_coeff && d->sim_damping)),
+               "NULL ensemble array");
+    TK_REQUIRE(!argmax || spectrum, "argmax needs the spectrum buffer");
+    int rc = check_device(device);
+    if (rc) return rc;
+    const long long S = d->size, L = d->layers, ncell = L * S * S, N = ncell * 4, nt = d->steps + 1;
+    TK_REQUIRE(N < (1LL << 24), "lattice too large for an SM-resident ensemble");
+    const size_t smem = tk::ensemble_smem_bytes((int)S, (int)L, (int)d->steps);
+    cudaDeviceProp prop;
+    TK_CUDA(cudaGetDeviceProperties(&prop, device));
+    TK_REQUIRE(smem <= (size_t)prop.sharedMemPerBlockOptin,
+               "ensemble state (%zu B) exceeds shared memory per CTA (%zu B); use a lattice plan", smem,
+               (size_t)prop.sharedMemPerBlockOptin);
+    if (d->n_sims == 0) return TK_OK;
+    for (long long i = 0; i < d->n_sims; ++i) {
+        TK_REQUIRE(d->sim_mask[i] >= 0 && d->sim_mask[i] < d->n_masks, "sim_mask[%lld] out of range", i);
+        TK_REQUIRE(d->sim_kick[i] >= 0 && d->sim_kick[i] < N, "sim_kick[%lld] out of range", i);
+    }
+    // dense attribute rows for the masks that carry mass / potential tags
+    std::vector<int> attr_row(d->n_masks, -1);
+    std::vector<double> attr_im, attr_v;
+    if (d->exc_offset) {
+        for (long long m = 0; m < d->n_masks; ++m) {
+            const int b = d->exc_offset[m], e = d->exc_offset[m + 1];
+            if (e <= b) continue;
+            attr_row[m] = (int)(attr_im.size() / N);
+            attr_im.resize(attr_im.size() + N, 1.0);
+            attr_v.resize(attr_v.size() + N, 0.0);
+            for (int k = b; k < e; ++k) {
+                TK_REQUIRE(d->exc_node[k] >= 0 && d->exc_node[k] < N, "exc_node out of range");
+                attr_im[attr_im.size() - N + d->exc_node[k]] = d->exc_inv_mass[k];
+                attr_v[attr_v.size() - N + d->exc_node[k]] = d->exc_potential[k];
+            }
+        }
+    }
+    std::vector<int> corr_off(d->n_masks + 1, 0);
+    long long ncorr = 0;
+    if (d->corr_offset) {
+        for (long long m = 0; m <= d->n_masks; ++m) corr_off[m] = d->corr_offset[m];
+        ncorr = corr_off[d->n_masks];
+        for (long long m = 0; m < d->n_masks; ++m)
+            TK_REQUIRE(corr_off[m + 1] - corr_off[m] <= tk::kEnsMaxCorr, "more than %d edge corrections in mask %lld",
+                       tk::kEnsMaxCorr, m);
+    }
+    std::vector<double> kickv(d->n_sims, 1.0);
+    if (d->sim_kick_value) kickv.assign(d->sim_kick_value, d->sim_kick_value + d->n_sims);
+
+    std::vector<void *> owned;
+    auto up = [&](auto **dst, const auto *src, size_t count) -> int {
+        using T = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+        T *p = nullptr;
+        TK_CUDA(cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T)));
+        owned.push_back(p);
+        if (count) TK_CUDA(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+        *dst = p;
+        return TK_OK;
+    };
+    tk::EnsDev P{};
+    P.S = (int)S; P.L = (int)L; P.n_masks = (int)d->n_masks; P.steps = (int)d->steps;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto cleanup = [&]() {
+        for (void *q : owned) cudaFree(q);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    };
+#define TK_ENS(x) do { rc = (x); if (rc) { cleanup(); return rc; } } while (0)
+    TK_ENS(up(&P.cell_bits, d->cell_bits, (size_t)d->n_masks * ncell));
+    TK_ENS(up(&P.attr_im, attr_im.data(), attr_im.size()));
+    TK_ENS(up(&P.attr_v, attr_v.data(), attr_v.size()));
+    TK_ENS(up(&P.mask_attr_row, attr_row.data(), attr_row.size()));
+    TK_ENS(up(&P.corr_off, corr_off.data(), corr_off.size()));
+    TK_ENS(up(&P.corr_a, d->corr_a, (size_t)ncorr));
+    TK_ENS(up(&P.corr_b, d->corr_b, (size_t)ncorr));
+    TK_ENS(up(&P.corr_sign, d->corr_sign, (size_t)ncorr));
+    TK_ENS(up(&P.sim_mask, d->sim_mask, (size_t)d->n_sims));
+    TK_ENS(up(&P.sim_kick, d->sim_kick, (size_t)d->n_sims));
+    TK_ENS(up(&P.sim_coeff, d->sim_coeff, (size_t)d->n_sims));
+    TK_ENS(up(&P.sim_damping, d->sim_damping, (size_t)d->n_sims));
+    TK_ENS(up(&P.sim_kick_value, kickv.data(), kickv.size()));
+    auto dalloc = [&](auto **dst, size_t count) -> int {
+        using T = std::remove_pointer_t<std::remove_pointer_t<decltype(dst)>>;
+        T *p = nullptr;
+        TK_CUDA(cudaMalloc((void **)&p, std::max<size_t>(count, 1) * sizeof(T)));
+        owned.push_back(p);
+        *dst = p;
+        return TK_OK;
+    };
+    TK_ENS(dalloc(&P.series, (size_t)d->n_sims * nt));
+    if (spectrum) TK_ENS(dalloc(&P.spectrum, (size_t)d->n_sims * nt));
+    if (argmax) TK_ENS(dalloc(&P.argmax, (size_t)d->n_sims));
+#define TK_ENS_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); \
+        return fail(TK_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while (0)
+    TK_ENS_CUDA(cudaFuncSetAttribute(tk::ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // threads: whole iterations over the cells, at most 448 per CTA
+    const long long iters = (ncell + 447) / 448;
+    int threads = (int)(((ncell + iters - 1) / iters + 31) / 32 * 32);
+    threads = std::max(64, std::min(threads, 448));
+    int occ = 1;
+    TK_ENS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk::ensemble_kernel, threads, smem));
+    const long long grid = std::min<long long>(d->n_sims, (long long)prop.multiProcessorCount * std::max(occ, 1));
+    TK_ENS_CUDA(cudaEventCreate(&e0));
+    TK_ENS_CUDA(cudaEventCreate(&e1));
+    TK_ENS_CUDA(cudaEventRecord(e0, 0));
+    tk::ensemble_kernel<<<(unsigned)grid, threads, smem>>>(P, d->n_sims);
+    TK_ENS_CUDA(cudaGetLastError());
+    TK_ENS_CUDA(cudaEventRecord(e1, 0));
+    TK_ENS_CUDA(cudaMemcpy(probe_series, P.series, (size_t)d->n_sims * nt * sizeof(double), cudaMemcpyDeviceToHost));
+    if (spectrum) TK_ENS_CUDA(cudaMemcpy(spectrum, P.spectrum, (size_t)d->n_sims * nt * sizeof(double), cudaMemcpyDeviceToHost));
+    if (argmax) TK_ENS_CUDA(cudaMemcpy(argmax, P.argmax, (size_t)d->n_sims * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (elapsed_ms) {
+        float ms = 0.f;
+        TK_ENS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *elapsed_ms = ms;
+    }
+    cleanup();
+    return TK_OK;
+#undef TK_ENS
+#undef TK_ENS_CUDA
 }
 
 }  // extern "C"

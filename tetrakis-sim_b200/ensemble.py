@@ -1,0 +1,156 @@
+"""Batched ensembles: many independent small-lattice simulations in one launch.
+
+The reference runs parameter sweeps as one Python process per point
+(``examples/naked_singularity_sweep.py:211-212``) and builds its eval dataset in a serial loop
+(``tetrakis_sim/evals/dataset.py:81-163``).  Here every simulation is one CTA of
+``ensemble_kernel`` (state resident in shared memory, probe DFT fused into the epilogue) behind
+``tk_ensemble_run`` in include/tetrakis_b200.h.  Each simulation is exactly what
+``run_wave_sim(G, steps, {kick: 1.0}, c, dt, damping)`` + ``run_fft(history, kick)`` compute for the
+graph ``apply_defect(build_sheet(...))``, including the per-simulation CFL clamp
+(``physics.py:74-91``; no warning is emitted per simulation -- ``stability_adjusted`` is returned).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .lattice import LatticeSpec
+
+
+@dataclass
+class EnsembleResult:
+    series: np.ndarray  # (n_sims, steps+1) probe (= kick node) time series
+    spectrum: np.ndarray  # (n_sims, steps+1) |DFT|
+    dominant_bin: np.ndarray  # (n_sims,) np.argmax(spectrum)
+    dominant_freq: np.ndarray  # (n_sims,) freq[argmax] with freq = fftfreq(steps+1, d=dt_eff)
+    effective_dt: np.ndarray  # (n_sims,)
+    stability_adjusted: np.ndarray  # (n_sims,) bool
+    max_degree: np.ndarray  # (n_sims,)
+    kick_nodes: list  # reference node tuples
+    elapsed_ms: float  # device time of the ensemble kernel
+    node_updates: int  # surviving nodes x steps summed over simulations
+
+
+def _spec_key(s: LatticeSpec):
+    return (s.size, s.dim, s.layers, s.defect, s.center, float(s.radius), float(s.mass),
+            float(s.potential), bool(s.prune_edges), s.wedge_layer)  # fmt: skip
+
+
+def mask_arrays(spec: LatticeSpec):
+    """(cell_bits[L*S*S] uint8, exceptions (node, inv_mass, potential), corrections, max_degree,
+    surviving node count) of one lattice+defect -- the per-mask inputs of ``tk_ensemble_run``."""
+    S, L = spec.size, spec.layers
+    alive = np.ones(spec.num_slots, dtype=bool)
+    part = np.ones(spec.num_slots, dtype=bool)
+    idx, flags, im, pot = spec.specials()
+    alive[idx] = (flags & 1) != 0
+    part[idx] = (flags & 2) != 0
+    part &= alive
+    A, P = alive.reshape(L, S, S, 4), part.reshape(L, S, S, 4)
+    w = np.array([1, 2, 4, 8], dtype=np.uint16)
+    bits = ((P * w).sum(-1) | ((A * w).sum(-1) << 4)).astype(np.uint8).reshape(-1)
+    Pi = P.astype(np.int64)
+    Pz = np.zeros((L + 2, S, S, 4), dtype=np.int64)
+    Pz[1:-1] = Pi
+    deg = Pi * ((Pi.sum(3, keepdims=True) - 1) + (Pi.sum(2, keepdims=True) - 1)
+                + (Pi.sum(1, keepdims=True) - 1) + Pz[:-2] + Pz[2:])  # fmt: skip
+    deg = deg.reshape(-1)
+    corr = spec.corrections()
+    for a, _, s in corr:
+        deg[a] += int(s)
+    max_degree = int(deg[alive].max()) if alive.any() else 0
+    keep = alive[idx] & ((im != 1.0) | (pot != 0.0))
+    exc = (idx[keep].astype(np.int32), im[keep], pot[keep])
+    return bits, exc, corr, max_degree, int(alive.sum())
+
+
+def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, device: int = 0,
+                 spectrum: bool = True) -> EnsembleResult:  # fmt: skip
+    """Run ``len(specs)`` independent simulations.  ``c``, ``dt``, ``damping`` are scalars or
+    per-simulation arrays; ``kicks`` optional list of node tuples (default: the batch.py kick rule).
+    All specs must share (size, dim, layers); identical defects share one device mask."""
+    specs = list(specs)
+    n = len(specs)
+    if n == 0:
+        raise ValueError("no simulations")
+    S, L, dim = specs[0].size, specs[0].layers, specs[0].dim
+    if any((s.size, s.layers, s.dim) != (S, L, dim) for s in specs):
+        raise ValueError("all simulations of an ensemble must share the lattice shape")
+    c = np.broadcast_to(np.asarray(c, dtype=np.float64), (n,))
+    dt = np.broadcast_to(np.asarray(dt, dtype=np.float64), (n,))
+    damping = np.ascontiguousarray(np.broadcast_to(np.asarray(damping, dtype=np.float64), (n,)))
+
+    masks: dict = {}
+    mask_data = []
+    sim_mask = np.empty(n, dtype=np.int32)
+    sim_kick = np.empty(n, dtype=np.int32)
+    kick_nodes = []
+    kick_cache: dict = {}
+    for i, s in enumerate(specs):
+        k = _spec_key(s)
+        if k not in masks:
+            masks[k] = len(mask_data)
+            mask_data.append(mask_arrays(s))
+            kick_cache[k] = s.kick_node()
+        sim_mask[i] = masks[k]
+        node = kicks[i] if kicks is not None else kick_cache[k]
+        if not s.contains(node):
+            raise ValueError(f"kick node {node} is not in the graph after defect application")
+        kick_nodes.append(node)
+        sim_kick[i] = s.index(node)
+    maxdeg = np.array([mask_data[m][3] for m in sim_mask], dtype=np.int64)
+    # physics.py:74-91 per simulation
+    eff = dt.astype(np.float64).copy()
+    limit = np.where(maxdeg > 0, 1.0 / np.sqrt(np.maximum(maxdeg, 1)), np.inf)
+    clamp = (maxdeg > 0) & (c > 0.0) & (c * eff > limit)
+    eff[clamp] = limit[clamp] / c[clamp]
+    coeff = np.ascontiguousarray((c * eff) ** 2)
+
+    n_masks = len(mask_data)
+    bits = np.ascontiguousarray(np.stack([m[0] for m in mask_data]))
+    exc_off = np.zeros(n_masks + 1, dtype=np.int32)
+    corr_off = np.zeros(n_masks + 1, dtype=np.int32)
+    for j, m in enumerate(mask_data):
+        exc_off[j + 1] = exc_off[j] + len(m[1][0])
+        corr_off[j + 1] = corr_off[j] + len(m[2])
+    exc_node = np.concatenate([m[1][0] for m in mask_data]).astype(np.int32)
+    exc_im = np.concatenate([m[1][1] for m in mask_data]).astype(np.float64)
+    exc_pot = np.concatenate([m[1][2] for m in mask_data]).astype(np.float64)
+    corr_a = np.array([a for m in mask_data for a, _, _ in m[2]], dtype=np.int32)
+    corr_b = np.array([b for m in mask_data for _, b, _ in m[2]], dtype=np.int32)
+    corr_s = np.array([s for m in mask_data for _, _, s in m[2]], dtype=np.float64)
+
+    nt = int(steps) + 1
+    series = np.empty((n, nt), dtype=np.float64)
+    spec_out = np.empty((n, nt), dtype=np.float64) if spectrum else None
+    arg = np.empty(n, dtype=np.int64) if spectrum else None
+    ms = ctypes.c_double(0.0)
+    p = _lib._p
+    d = _lib.EnsembleDesc(S, L, n_masks, p(bits), p(exc_off), p(exc_node), p(exc_im), p(exc_pot),
+                          p(corr_off), p(corr_a), p(corr_b), p(corr_s), n, p(sim_mask), p(sim_kick),
+                          None, p(coeff), p(damping), int(steps))  # fmt: skip
+    _lib.check(_lib.lib().tk_ensemble_run(device, ctypes.byref(d), p(series), p(spec_out), p(arg),
+                                          ctypes.byref(ms)))  # fmt: skip
+    if spectrum:
+        freq = np.fft.fftfreq(nt)[arg] / eff  # fftfreq(nt, d=dt)[k] == fftfreq(nt)[k] / dt
+    else:
+        freq = None
+    updates = int(sum(mask_data[m][4] for m in sim_mask)) * int(steps)
+    return EnsembleResult(series, spec_out, arg, freq, eff, clamp, maxdeg, kick_nodes, ms.value, updates)
+
+
+def sweep_grid(size: int, layers: int, radii, dampings, dts, *, dim: int = 3, defect="blackhole",
+               **defect_kw):
+    """Specs + per-simulation (damping, dt) arrays for a radius x damping x dt grid (BASELINE config 5).
+    Ordering: radius-major, then damping, then dt."""
+    radii, dampings, dts = map(lambda a: np.asarray(a, dtype=np.float64), (radii, dampings, dts))
+    base = [LatticeSpec(size=size, dim=dim, layers=layers, defect=defect, radius=float(r), **defect_kw)
+            for r in radii]  # fmt: skip
+    specs = [base[i] for i in range(len(radii)) for _ in range(len(dampings) * len(dts))]
+    damp = np.tile(np.repeat(dampings, len(dts)), len(radii))
+    dt = np.tile(dts, len(radii) * len(dampings))
+    return specs, damp, dt

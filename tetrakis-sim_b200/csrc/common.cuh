@@ -61,6 +61,11 @@ __device__ __forceinline__ void st256(double *p, const double v[4])
                  :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 // 16-byte asynchronous global->shared copy (LDGSTS); ok == false writes zeros and reads nothing.
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool ok)
 {

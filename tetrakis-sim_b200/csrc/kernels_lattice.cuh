@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256, MINB)
 lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
                 double *__restrict__ w, double *__restrict__ prow, double *__restrict__ pcol,
                 double coeff, double damping, int zl_begin, int zl_end, int rchunk, int nchunk,
-                int nsegk, int nct, int nzg)
+                int nsegk, int nct, int nzg, int pf_rows)
 {
     constexpr int WZ = 8 / WC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,8 +156,24 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
     const int r_end = min(S, r_begin + rchunk);
     const int tab0 = c0 / kTabSeg;  // all CPL cells of a lane share a table segment (CPL | 64)
 
+    // L2 prefetch `pf_rows` rows ahead (one request per 128-byte line): turns the HBM latency of the
+    // streamed rows into an L2 hit without spending registers on software pipelining.
+    const bool pf_lane = MODE == 0 && pf_rows > 0 && valid[0] && ((lane * CPL) & 3) == 0;
+    if (pf_lane) {
+        for (int r = r_begin; r < min(r_end, r_begin + pf_rows); ++r) {
+            const size_t o = zbase + ((size_t)r * S + c0) * 4;
+            prefetch_l2(u + o);
+            prefetch_l2(w + o);
+        }
+    }
+
     for (int r = r_begin; r < r_end; ++r) {
         const size_t rowoff = zbase + ((size_t)r * S + c0) * 4;
+        if (pf_lane && r + pf_rows < r_end) {
+            const size_t o = rowoff + (size_t)pf_rows * S * 4;
+            prefetch_l2(u + o);
+            prefetch_l2(w + o);
+        }
         double uq[CPL][4], upq[CPL][4], zm[CPL][4], zp[CPL][4];
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
@@ -442,23 +458,33 @@ lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, int nrowblk,
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         if (lane < 4) rowinfo[line * 8 + lane] = acc;
     } else {
-        const long long t = (long long)(blockIdx.x - nrowblk) * blockDim.x + threadIdx.x;
-        if (t >= nline * 4) return;
-        const long long line = t >> 2;  // zl*S + c
-        const int q = (int)(t & 3);
-        const long long zl = line / S, c = line % S;
-        const double *p = pcol + ((size_t)zl * nchunk * S + c) * 4 + q;
-        const size_t stride = (size_t)S * 4;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int k = 0;
-        for (; k + 3 < nchunk; k += 4) {
-            a0 += p[(size_t)k * stride];
-            a1 += p[(size_t)(k + 1) * stride];
-            a2 += p[(size_t)(k + 2) * stride];
-            a3 += p[(size_t)(k + 3) * stride];
+        // 32 (column, quadrant) values x 8 chunk slices per CTA; slices combined in fixed order
+        __shared__ double part[8][32];
+        const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+        const long long t = (long long)(blockIdx.x - nrowblk) * 32 + lane;
+        double acc = 0.0;
+        if (t < nline * 4) {
+            const long long line = t >> 2;  // zl*S + c
+            const int q = (int)(t & 3);
+            const long long zl = line / S, c = line % S;
+            const double *p = pcol + ((size_t)zl * nchunk * S + c) * 4 + q;
+            const size_t stride = (size_t)S * 4;
+            double a0 = 0.0, a1 = 0.0;
+            int k = slice;
+            for (; k + 8 < nchunk; k += 16) {
+                a0 += p[(size_t)k * stride];
+                a1 += p[(size_t)(k + 8) * stride];
+            }
+            if (k < nchunk) a0 += p[(size_t)k * stride];
+            acc = a0 + a1;
         }
-        for (; k < nchunk; ++k) a0 += p[(size_t)k * stride];
-        colinfo[line * 8 + q] = (a0 + a1) + (a2 + a3);
+        part[slice][lane] = acc;
+        __syncthreads();
+        if (slice == 0 && t < nline * 4) {
+            const double s01 = part[0][lane] + part[1][lane], s23 = part[2][lane] + part[3][lane];
+            const double s45 = part[4][lane] + part[5][lane], s67 = part[6][lane] + part[7][lane];
+            colinfo[(t >> 2) * 8 + (t & 3)] = (s01 + s23) + (s45 + s67);
+        }
     }
 }
 

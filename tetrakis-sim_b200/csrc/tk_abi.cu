@@ -115,6 +115,7 @@ struct tk_plan {
     double *rowinfo = nullptr, *colinfo = nullptr, *prow = nullptr, *pcol = nullptr;
     int cpl = 2, wc = 8, rchunk = 64, nchunk = 1, nsegk = 1;
     int wz3d = 0, stages3d = 0, minb3d = 2;  // wz3d > 0: 3-D steps use lat_step3d_kernel<wz3d, stages3d, minb3d>
+    int pf_rows = 0;                         // register path: L2 prefetch distance in rows (0 = off)
     int minb = 1;                            // register path: min resident CTAs per SM asked of ptxas
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
@@ -171,7 +172,7 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
     if (grid > 0x7fffffffLL) return fail(TK_ERR_INVALID, "lattice grid too large");
     tk::lat_step_kernel<CPL, WC, K3D, MODE, MINB><<<(unsigned)grid, 256, 0, p->stream>>>(
         p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
-        zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg);
+        zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg, p->pf_rows);
     p->launches++;
     TK_CUDA(cudaGetLastError());
     return TK_OK;
@@ -294,7 +295,7 @@ int lat_finalise(tk_plan *p, const double *state, double *probe_row)
 {
     const long long nline = (long long)p->lat.Lloc * p->lat.S;
     const int nrowblk = (int)((nline + 7) / 8);
-    const int ncolblk = (int)((nline * 4 + 255) / 256);
+    const int ncolblk = (int)((nline * 4 + 31) / 32);
     tk::lat_finalise_kernel<<<(unsigned)(nrowblk + ncolblk), 256, 0, p->stream>>>(
         p->lat.S, p->lat.Lloc, p->nsegk, p->nchunk, nrowblk, p->prow, p->pcol, p->rowinfo, p->colinfo,
         state, p->probe_idx, probe_row ? p->n_probes : 0, probe_row);
@@ -621,7 +622,8 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     p->wc = env_int("TK_LAT_WC", halo ? 1 : 8);
     if (p->cpl != 1 && p->cpl != 2 && p->cpl != 4) p->cpl = 2;
     p->minb = env_int("TK_LAT_MINB", 1);
-    if (halo && env_int("TK_LAT3D", 1)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
+    p->pf_rows = env_int("TK_LAT_PREFETCH", 0);
+    if (halo && env_int("TK_LAT3D", 0)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
         p->wz3d = env_int("TK_LAT3D_WZ", 8);
         p->stages3d = env_int("TK_LAT3D_STAGES", 4);
         p->minb3d = env_int("TK_LAT3D_MINB", p->wz3d == 16 ? 1 : (p->wz3d == 4 ? 4 : 2));

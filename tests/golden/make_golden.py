@@ -201,5 +201,54 @@ def main():
                  kick="bench", snapshots=[0, 50, 500, 1000, 2000])
 
 
+def cli_goldens():
+    """Artefacts of the reference's own entry points (tetrakis-batch, tetrakis-eval generate)."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+
+    from tetrakis_sim import batch as ref_batch
+    from tetrakis_sim.evals.dataset import generate_defect_classification_jsonl
+
+    tmp = tempfile.mkdtemp()
+    try:
+        for tag, argv in {
+            "batch_cfg1": ["--dim", "3", "--size", "11", "--layers", "7", "--radius", "2.5", "--steps", "50"],
+            "batch_sing2d": ["--dim", "2", "--size", "9", "--steps", "30", "--defect_type", "singularity",
+                             "--radius", "1.5", "--sing_mass", "200", "--sing_potential", "2.5",
+                             "--sing_prune_edges", "--damping", "0.01"],
+            "batch_wedge3d": ["--dim", "3", "--size", "7", "--layers", "5", "--steps", "25",
+                              "--defect_type", "wedge", "--dt", "0.15"],
+        }.items():
+            old = sys.argv
+            sys.argv = ["tetrakis-batch", *argv, "--outdir", tmp, "--prefix", tag]
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref_batch.main()
+            sys.argv = old
+            shutil.copy(os.path.join(tmp, f"{tag}_spectrum.csv"), os.path.join(HERE, f"{tag}_spectrum.csv"))
+            meta = json.load(open(os.path.join(tmp, f"{tag}_metadata.json")))
+            for k in ("run_id", "outdir", "csv_filename", "plot_filename"):
+                meta.pop(k, None)
+            meta["argv"] = argv
+            json.dump(meta, open(os.path.join(HERE, f"{tag}_metadata.json"), "w"), indent=1, sort_keys=True)
+            print("batch golden", tag)
+        for tag, kw in {
+            "evals_2d": dict(n_per_class=3, seed=0, size=9, dim=2, layers=5, steps=30, c=1.0, dt=0.2, damping=0.0),
+            "evals_3d": dict(n_per_class=2, seed=5, size=7, dim=3, layers=5, steps=20, c=1.0, dt=0.3, damping=0.01),
+        }.items():
+            out = os.path.join(HERE, f"{tag}.jsonl")
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                generate_defect_classification_jsonl(out, **kw)
+            json.dump(kw, open(os.path.join(HERE, f"{tag}_args.json"), "w"))
+            print("evals golden", tag)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--cli-only" not in sys.argv:
+        main()
+    cli_goldens()

@@ -82,14 +82,19 @@ def test_structured_kernel_matches_the_reference(name, route):
     assert rel_inf(states, g["states"]) < tol
 
 
-VARIANTS = [(1, 8, 16), (1, 2, 32), (1, 1, 64), (2, 8, 16), (2, 2, 32), (2, 1, 256), (4, 8, 32), (4, 1, 16)]
+# (cells/lane, segments/CTA, rows/CTA, min CTAs/SM, L2 prefetch distance in rows)
+VARIANTS = [(1, 8, 16, 3, 2), (1, 2, 32, 3, 0), (1, 1, 64, 3, 5), (2, 8, 16, 1, 2), (2, 2, 32, 1, 1),
+            (2, 1, 256, 2, 3), (4, 8, 32, 1, 2), (4, 1, 16, 1, 20), (1, 8, 40, 2, 4), (1, 8, 24, 4, 1),
+            (1, 1, 19, 4, 2), (1, 1, 33, 2, 7), (2, 8, 50, 2, 2)]
 
 
-@pytest.mark.parametrize("cpl,wc,rchunk", VARIANTS)
+@pytest.mark.parametrize("cpl,wc,rchunk,minb,pf", VARIANTS)
 @pytest.mark.parametrize("case", ["2d_hole", "3d_sing", "3d_wedge_odd"])
-def test_every_kernel_variant_against_the_oracle(cpl, wc, rchunk, case, monkeypatch):
+def test_every_kernel_variant_against_the_oracle(cpl, wc, rchunk, minb, pf, case, monkeypatch):
     """Medium lattices (several segments, ragged tails, many row chunks) vs the C oracle."""
     monkeypatch.setenv("TK_LAT3D", "0")  # the register-path kernel, also for the 3-D cases
+    monkeypatch.setenv("TK_LAT_MINB", str(minb))
+    monkeypatch.setenv("TK_LAT_PREFETCH", str(pf))
     _variant_case(cpl, wc, rchunk, case, monkeypatch)
 
 
@@ -99,6 +104,7 @@ def test_every_kernel_variant_against_the_oracle(cpl, wc, rchunk, case, monkeypa
 def test_3d_staged_kernel_variants_against_the_oracle(wz, stages, rchunk, case, monkeypatch):
     """lat_step3d_kernel (cp.async-staged z neighbours): partial z-groups, ragged segments, short
     and long row chunks (fewer rows than pipeline stages included)."""
+    monkeypatch.setenv("TK_LAT3D", "1")
     monkeypatch.setenv("TK_LAT3D_WZ", str(wz))
     monkeypatch.setenv("TK_LAT3D_STAGES", str(stages))
     _variant_case(1, 1, rchunk, case, monkeypatch)

@@ -178,24 +178,40 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
     return TK_OK;
 }
 
+// (cells per lane, segments per CTA, min resident CTAs per SM asked of ptxas)
+#define TK_LAT_VARIANTS(X)                                                                        \
+    X(1, 8, 2) X(1, 8, 3) X(1, 8, 4) X(1, 1, 2) X(1, 1, 3) X(1, 1, 4) X(1, 2, 2) X(1, 2, 3) \
+    X(2, 8, 1) X(2, 8, 2) X(2, 1, 1) X(2, 1, 2) X(2, 2, 1) X(4, 8, 1) X(4, 1, 1)
+
+bool lat_supported(int cpl, int wc, int mb)
+{
+#define X(CPL, WC, MB) if (cpl == CPL && wc == WC && mb == MB) return true;
+    TK_LAT_VARIANTS(X)
+#undef X
+    return false;
+}
+
 template <int MODE>
 int launch_lat_dispatch(tk_plan *p, int zl_begin, int zl_end)
 {
     const bool k3d = p->lat.halo != 0;
-    if (MODE == 0 && k3d && p->cpl == 1 && p->minb == 3) {  // register path squeezed to 3 CTAs/SM
-        if (p->wc == 1) return launch_lat<1, 1, true, 0, 3>(p, zl_begin, zl_end);
-        if (p->wc == 2) return launch_lat<1, 2, true, 0, 3>(p, zl_begin, zl_end);
-        if (p->wc == 8) return launch_lat<1, 8, true, 0, 3>(p, zl_begin, zl_end);
+    if (MODE != 0) {  // sums-only pass: register pressure is irrelevant, one instantiation per shape
+#define X(CPL, WC, MB)                                                        \
+    if (p->cpl == CPL && p->wc == WC && p->minb == MB)                        \
+        return k3d ? launch_lat<CPL, WC, true, 1, 1>(p, zl_begin, zl_end)     \
+                   : launch_lat<CPL, WC, false, 1, 1>(p, zl_begin, zl_end);
+        TK_LAT_VARIANTS(X)
+#undef X
+    } else {
+#define X(CPL, WC, MB)                                                        \
+    if (p->cpl == CPL && p->wc == WC && p->minb == MB)                        \
+        return k3d ? launch_lat<CPL, WC, true, 0, MB>(p, zl_begin, zl_end)    \
+                   : launch_lat<CPL, WC, false, 0, MB>(p, zl_begin, zl_end);
+        TK_LAT_VARIANTS(X)
+#undef X
     }
-#define TK_CASE(CPL, WC)                                                         \
-    if (p->cpl == CPL && p->wc == WC)                                            \
-        return k3d ? launch_lat<CPL, WC, true, MODE>(p, zl_begin, zl_end)        \
-                   : launch_lat<CPL, WC, false, MODE>(p, zl_begin, zl_end);
-    TK_CASE(1, 8) TK_CASE(1, 2) TK_CASE(1, 1)
-    TK_CASE(2, 8) TK_CASE(2, 2) TK_CASE(2, 1)
-    TK_CASE(4, 8) TK_CASE(4, 1)
-#undef TK_CASE
-    return fail(TK_ERR_INVALID, "unsupported lattice kernel variant cpl=%d wc=%d", p->cpl, p->wc);
+    return fail(TK_ERR_INVALID, "unsupported lattice kernel variant cpl=%d wc=%d minb=%d", p->cpl, p->wc,
+                p->minb);
 }
 
 template <int WZ, int STAGES>
@@ -268,11 +284,11 @@ int launch_lat3d_dispatch(tk_plan *p, int zl_begin, int zl_end)
                 p->stages3d, p->minb3d);
 }
 
-template <int CPL, int WC, bool K3D>
+template <int CPL, int WC, bool K3D, int MB>
 int lat_occ_one()
 {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tk::lat_step_kernel<CPL, WC, K3D, 0>, 256, 0) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tk::lat_step_kernel<CPL, WC, K3D, 0, MB>, 256, 0) != cudaSuccess) {
         cudaGetLastError();
         n = 2;
     }
@@ -280,14 +296,12 @@ int lat_occ_one()
 }
 
 // resident CTAs per SM of the step kernel variant in use
-int lat_occupancy(int cpl, int wc, bool k3d)
+int lat_occupancy(int cpl, int wc, int mb, bool k3d)
 {
-#define TK_CASE(CPL, WC) \
-    if (cpl == CPL && wc == WC) return k3d ? lat_occ_one<CPL, WC, true>() : lat_occ_one<CPL, WC, false>();
-    TK_CASE(1, 8) TK_CASE(1, 2) TK_CASE(1, 1)
-    TK_CASE(2, 8) TK_CASE(2, 2) TK_CASE(2, 1)
-    TK_CASE(4, 8) TK_CASE(4, 1)
-#undef TK_CASE
+#define X(CPL, WC, MB) \
+    if (cpl == CPL && wc == WC && mb == MB) return k3d ? lat_occ_one<CPL, WC, true, MB>() : lat_occ_one<CPL, WC, false, MB>();
+    TK_LAT_VARIANTS(X)
+#undef X
     return 2;
 }
 
@@ -620,9 +634,9 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     // ---- kernel variant + tiling
     p->cpl = env_int("TK_LAT_CPL", 1);
     p->wc = env_int("TK_LAT_WC", halo ? 1 : 8);
-    if (p->cpl != 1 && p->cpl != 2 && p->cpl != 4) p->cpl = 2;
-    p->minb = env_int("TK_LAT_MINB", 1);
-    p->pf_rows = env_int("TK_LAT_PREFETCH", 0);
+    p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? 3 : 1);
+    p->pf_rows = env_int("TK_LAT_PREFETCH", 2);
+    if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 1; p->wc = halo ? 1 : 8; p->minb = 3; }
     if (halo && env_int("TK_LAT3D", 0)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
         p->wz3d = env_int("TK_LAT3D_WZ", 8);
         p->stages3d = env_int("TK_LAT3D_STAGES", 4);
@@ -642,7 +656,7 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
         const long long nzg = (Lloc + wz - 1) / wz;
         const long long slots =
             (long long)p->sm_count * (p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d, p->minb3d)
-                                              : lat_occupancy(p->cpl, p->wc, halo != 0));
+                                              : lat_occupancy(p->cpl, p->wc, p->minb, halo != 0));
         int best = 16;
         double best_eff = -1.0;
         for (int rc_ = 16; rc_ <= 256 && rc_ <= std::max<long long>(16, S); ++rc_) {
@@ -985,7 +999,7 @@ int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchu
     if (wc) *wc = p->wz3d ? -p->wz3d * 100 - p->stages3d : p->wc;  // 3-D: -(100*layers_per_cta + stages)
     if (rchunk) *rchunk = p->rchunk;
     if (occ) *occ = p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d, p->minb3d)
-                            : lat_occupancy(p->cpl, p->wc, p->lat.halo != 0);
+                            : lat_occupancy(p->cpl, p->wc, p->minb, p->lat.halo != 0);
     return TK_OK;
 }
 

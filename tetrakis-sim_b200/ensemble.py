@@ -40,7 +40,7 @@ def _spec_key(s: LatticeSpec):
             float(s.potential), bool(s.prune_edges), s.wedge_layer)  # fmt: skip
 
 
-def mask_arrays(spec: LatticeSpec):
+def mask_arrays(spec: LatticeSpec, want_degrees: bool = False):
     """(cell_bits[L*S*S] uint8, exceptions (node, inv_mass, potential), corrections, max_degree,
     surviving node count) of one lattice+defect -- the per-mask inputs of ``tk_ensemble_run``."""
     S, L = spec.size, spec.layers
@@ -65,6 +65,8 @@ def mask_arrays(spec: LatticeSpec):
     max_degree = int(deg[alive].max()) if alive.any() else 0
     keep = alive[idx] & ((im != 1.0) | (pot != 0.0))
     exc = (idx[keep].astype(np.int32), im[keep], pot[keep])
+    if want_degrees:
+        return bits, exc, corr, max_degree, int(alive.sum()), deg, alive
     return bits, exc, corr, max_degree, int(alive.sum())
 
 

@@ -634,8 +634,10 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     // ---- kernel variant + tiling
     p->cpl = env_int("TK_LAT_CPL", 1);
     p->wc = env_int("TK_LAT_WC", halo ? 1 : 8);
-    p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? 3 : 1);
-    p->pf_rows = env_int("TK_LAT_PREFETCH", 2);
+    // defaults from the round-1 sweeps on B200 (profiles/r01_sweeps.md): 2-D 3 CTAs/SM + 1-row L2
+    // prefetch; 3-D 2 CTAs/SM + 2-row prefetch
+    p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? (halo ? 2 : 3) : 1);
+    p->pf_rows = env_int("TK_LAT_PREFETCH", halo ? 2 : 1);
     if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 1; p->wc = halo ? 1 : 8; p->minb = 3; }
     if (halo && env_int("TK_LAT3D", 0)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
         p->wz3d = env_int("TK_LAT3D_WZ", 8);

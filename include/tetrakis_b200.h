@@ -113,7 +113,11 @@ typedef struct tk_run_args {
     const int64_t *probe_index; /* local node indices */
     double *probe_out;          /* host, (steps+1) x n_probes, row 0 = state before the first step */
     double *history_out;        /* host or NULL, (steps+1) x num_nodes (physics.py:104,129) */
-    double *energy_out;         /* host or NULL, (steps+1): discrete energy (not in the reference) */
+    double *energy_out;         /* host or NULL, `steps` values: entry s is the staggered discrete energy
+                                   between states s and s+1,
+                                     1/2 sum_i [ m_i (u_i^{s+1}-u_i^s)^2 / coeff + u_i^{s+1} ((V u^s)_i - (L u^s)_i) ]
+                                   (x c^2 for physical units); exactly conserved when damping = 0.
+                                   A new diagnostic: the reference computes no energy. */
     double *elapsed_ms;         /* host or NULL: device time of the stepping loop (CUDA events) */
     double *step_kernel_ms;     /* host or NULL: summed CUDA-event time of the step kernels alone */
 } tk_run_args;
@@ -142,6 +146,10 @@ int tk_lattice_halo_ptrs(tk_plan *plan, int32_t next_state, void **send_lo, void
 int tk_lattice_step_begin(tk_plan *plan, double coeff, double damping);
 /* Update local layers [zl_begin, zl_end) (reads the current halos). */
 int tk_lattice_step_layers(tk_plan *plan, int32_t zl_begin, int32_t zl_end);
+/* Same, launched on another stream (e.g. a high-priority side stream for the two boundary layers so
+ * that they run concurrently with the interior layers); ordering against tk_lattice_step_end is the
+ * caller's job (events). */
+int tk_lattice_step_layers_on(tk_plan *plan, int32_t zl_begin, int32_t zl_end, void *cuda_stream);
 /* After every layer was updated: finish the row/column sums of the new state, swap buffers. */
 int tk_lattice_step_end(tk_plan *plan);
 

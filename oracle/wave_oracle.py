@@ -312,6 +312,25 @@ def run_structured(
     return {"u": u, "uprev": up, "probes": pout}
 
 
+def staggered_energy(history, rowptr, colidx, deg, inv_mass, potential, coeff):
+    """Discrete energy between consecutive states of a (steps+1, N) history (NOT in the reference --
+    a new diagnostic): entry s =
+        1/2 sum_i [ m_i (u_i^{s+1} - u_i^s)^2 / coeff + u_i^{s+1} (V_i u_i^s - lap_i(u^s)) ],
+    lap = A u - deg * u as in physics.py:115-119.  Exactly conserved by the undamped leapfrog."""
+    import scipy.sparse as sp
+
+    h = np.asarray(history, dtype=np.longdouble)
+    n = h.shape[1]
+    A = sp.csr_matrix((np.ones(len(colidx)), np.asarray(colidx), np.asarray(rowptr)), shape=(n, n))
+    out = np.empty(h.shape[0] - 1, dtype=np.float64)
+    m = 1.0 / np.asarray(inv_mass, dtype=np.longdouble)
+    for s in range(h.shape[0] - 1):
+        u, un = h[s], h[s + 1]
+        lap = (A @ np.asarray(u, dtype=np.float64)).astype(np.longdouble) - np.asarray(deg) * u
+        out[s] = float(0.5 * np.sum(m * (un - u) ** 2 / coeff + un * (np.asarray(potential) * u - lap)))
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # physics.py:140-165
 # --------------------------------------------------------------------------------------

@@ -266,3 +266,41 @@ def test_size_independent_properties_on_a_large_lattice():
     assert np.max(np.abs(back)) < 1e-9  # u_{-1} = 0
     expect[spec.index(k1)] = 1.0
     assert np.max(np.abs(back_prev - expect)) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["t2d_s7_sing_m50_v25", "t3d_s7l5_sing_prune_v3", "random_graph_multi_kick",
+                                  "cfg1_s11l7_blackhole_r2p5", "t3d_s7l5_wedge"])
+def test_energy_series_matches_the_oracle_on_both_kernels(name):
+    """The energy diagnostic (not in the reference): both kernels against a longdouble evaluation of
+    the same formula on the reference's own history."""
+    g = load_golden(name)
+    G, labels = graph_from_golden(g)
+    if name == "random_graph_multi_kick":
+        G.add_edge(5, 5)
+    init = _initial_data(g, labels)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        h = tk.run_wave_sim(G, steps=g["steps"], initial_data=init, c=g["c"], dt=g["dt"],
+                            damping=g["damping"], energy=True)
+    coeff = (g["c"] * g["effective_dt"]) ** 2
+    ref = wo.staggered_energy(h.array, g["rowptr"], g["colidx"], g["deg"], g["inv_mass"], g["potential"],
+                              coeff) * g["c"] ** 2
+    assert h.energy.shape == (g["steps"],)
+    assert rel_inf(h.energy, ref) < 1e-11
+    if g["lattice"]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            hs = tk.run_wave_sim(_spec_from(g["lattice"]), steps=g["steps"], initial_data=init, c=g["c"],
+                                 dt=g["dt"], damping=g["damping"], energy=True)
+        assert rel_inf(hs.energy, ref) < 1e-11
+
+
+def test_energy_is_conserved_without_damping_and_decays_with_it():
+    spec = tk.LatticeSpec(size=300, dim=3, layers=9, defect="blackhole", radius=4.5)
+    k = spec.kick_node()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        h0 = tk.run_wave_sim(spec, steps=200, initial_data={k: 1.0}, dt=0.01, energy=True)
+        h1 = tk.run_wave_sim(spec, steps=200, initial_data={k: 1.0}, dt=0.01, damping=0.01, energy=True)
+    assert np.max(np.abs(h0.energy - h0.energy[0])) < 1e-10 * abs(h0.energy[0])
+    assert h0.energy[0] > 0 and np.all(np.diff(h1.energy) < 0)

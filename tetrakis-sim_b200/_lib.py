@@ -25,7 +25,7 @@ ABI_SYMBOLS = (
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
     "tk_plan_run", "tk_plan_launch_count", "tk_plan_destroy",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
-    "tk_lattice_step_end", "tk_lattice_tiling", "tk_dft_abs", "tk_ensemble_run",
+    "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling", "tk_dft_abs", "tk_ensemble_run",
 )  # fmt: skip
 
 
@@ -107,6 +107,7 @@ def lib():
                                        POINTER(c_int64)]  # fmt: skip
     L.tk_lattice_step_begin.argtypes = [P, c_double, c_double]
     L.tk_lattice_step_layers.argtypes = [P, c_int32, c_int32]
+    L.tk_lattice_step_layers_on.argtypes = [P, c_int32, c_int32, P]
     L.tk_lattice_step_end.argtypes = [P]
     L.tk_lattice_tiling.argtypes = [P, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                                     POINTER(c_int32)]  # fmt: skip
@@ -273,8 +274,8 @@ class Plan:
 
     # -- stepping -----------------------------------------------------------------------------
     def run(self, steps, coeff, damping, *, probes=None, history=False, timed=False,
-            probe_out=None, history_out=None):  # fmt: skip
-        """``steps`` leapfrog updates.  Returns dict(probes, history, elapsed_ms)."""
+            probe_out=None, history_out=None, energy=False):  # fmt: skip
+        """``steps`` leapfrog updates.  Returns dict(probes, history, energy, elapsed_ms, ...)."""
         steps = int(steps)
         pidx = _arr(probes if probes is not None else [], np.int64)
         pout = None
@@ -285,11 +286,13 @@ class Plan:
             hout = (history_out if history_out is not None
                     else np.empty((steps + 1, self.num_nodes), dtype=np.float64))  # fmt: skip
         ms, kms = c_double(0.0), c_double(0.0)
+        eout = np.empty(steps, dtype=np.float64) if energy else None
         a = RunArgs(steps, float(coeff), float(damping), len(pidx), _p(pidx), _p(pout), _p(hout),
-                    None, ctypes.cast(ctypes.byref(ms), c_void_p) if timed else None,
+                    _p(eout), ctypes.cast(ctypes.byref(ms), c_void_p) if timed else None,
                     ctypes.cast(ctypes.byref(kms), c_void_p) if timed else None)  # fmt: skip
         check(lib().tk_plan_run(self._h, ctypes.byref(a)))
-        return {"probes": pout, "history": hout, "elapsed_ms": ms.value if timed else None,
+        return {"probes": pout, "history": hout, "energy": eout,
+                "elapsed_ms": ms.value if timed else None,
                 "step_kernel_ms": kms.value if timed else None}
 
     # -- slab phases (multi-GPU) --------------------------------------------------------------
@@ -306,6 +309,9 @@ class Plan:
 
     def step_layers(self, zl_begin, zl_end):
         check(lib().tk_lattice_step_layers(self._h, int(zl_begin), int(zl_end)))
+
+    def step_layers_on(self, zl_begin, zl_end, cuda_stream: int):
+        check(lib().tk_lattice_step_layers_on(self._h, int(zl_begin), int(zl_end), c_void_p(cuda_stream)))
 
     def step_end(self):
         check(lib().tk_lattice_step_end(self._h))

@@ -11,14 +11,17 @@
 
 namespace tk {
 
+template <bool KEN>
 __global__ void __launch_bounds__(256)
 graph_step_kernel(long long n, const long long *__restrict__ slice_off,
                   const int *__restrict__ ell_idx, const double *__restrict__ deg,
                   const double *__restrict__ inv_mass, const double *__restrict__ potential,
-                  const double *__restrict__ u, double *__restrict__ w, double coeff, double damping)
+                  const double *__restrict__ u, double *__restrict__ w, double coeff, double damping,
+                  double *__restrict__ pen, double inv_coeff)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    double e = 0.0;
+    if (i < n) {
     const long long slice = i >> 5;
     const int lane = (int)(i & 31);
     const long long off = slice_off[slice];
@@ -37,8 +40,35 @@ graph_step_kernel(long long n, const long long *__restrict__ slice_off,
     for (; k < width; ++k) nsum = __dadd_rn(nsum, u[idx[(size_t)k * 32]]);
     const double ui = u[i];
     const double lap = __dsub_rn(nsum, __dmul_rn(deg[i], ui));  // physics.py:119
-    w[i] = leap_exact(ui, w[i], __dmul_rn(coeff, inv_mass[i]), lap, __dmul_rn(coeff, potential[i]),
-                      damping);
+    const double un = leap_exact(ui, w[i], __dmul_rn(coeff, inv_mass[i]), lap,
+                                 __dmul_rn(coeff, potential[i]), damping);
+    w[i] = un;
+    if (KEN) e = (un - ui) * (un - ui) * inv_coeff / inv_mass[i] + un * (potential[i] * ui - lap);
+    }
+    if (KEN) {  // per-CTA partial of twice the staggered energy (fixed tree => deterministic)
+        __shared__ double red[8];
+        e = warp_sum(e);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            pen[blockIdx.x] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    }
+}
+
+// energy_out = 1/2 * sum(pen[0..n)) in a fixed order
+__global__ void __launch_bounds__(256)
+energy_reduce_kernel(const double *__restrict__ pen, long long n, double *__restrict__ energy_out)
+{
+    __shared__ double red[256];
+    double a = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) a += pen[i];
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *energy_out = 0.5 * red[0];
 }
 
 // |DFT| of real series, arbitrary length (reference physics.py:163: np.abs(np.fft.fft(values))).

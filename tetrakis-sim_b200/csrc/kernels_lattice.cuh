@@ -56,14 +56,17 @@ __device__ __forceinline__ unsigned plain_flags(const LatDev &P, int zl)
 struct CellIO {
     double uq[4], upq[4], zm[4], zp[4], RS[4], RC[4], CS[4], CC[4];
     double un[4], pun[4];
+    double e;  // sum over the cell of m (u+ - u)^2 / coeff + u+ (V u - lap): twice the staggered energy
 };
 
 //   io.un[q] <- u_{t+1};  io.pun[q] <- participation-masked u_{t+1} (what row/col sums accumulate)
 __device__ __noinline__ void cell_update_detail(const LatDev &P, const double *__restrict__ ustate,
                                                 int det, int cell_in_tab, long long node0,
-                                                unsigned f, double coeff, double damping, CellIO &io)
+                                                unsigned f, double coeff, double damping,
+                                                double inv_coeff, CellIO &io)
 {
     double cell = 0.0;
+    io.e = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         if ((f >> q) & 1u) cell += io.uq[q];
@@ -97,6 +100,7 @@ __device__ __noinline__ void cell_update_detail(const LatDev &P, const double *_
         const double r = 2.0 * uq - upq + (coeff * im) * lap - (coeff * v) * uq - damping * (uq - upq);
         io.un[q] = alive ? r : 0.0;
         io.pun[q] = part ? io.un[q] : 0.0;
+        if (alive) io.e += (r - uq) * (r - uq) * inv_coeff / im + r * (v * uq - lap);
     }
 }
 
@@ -106,9 +110,11 @@ __global__ void __launch_bounds__(256, MINB)
 lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
                 double *__restrict__ w, double *__restrict__ prow, double *__restrict__ pcol,
                 double coeff, double damping, int zl_begin, int zl_end, int rchunk, int nchunk,
-                int nsegk, int nct, int nzg, int pf_rows)
+                int nsegk, int nct, int nzg, int pf_rows, double *__restrict__ pen, double inv_coeff)
 {
     constexpr int WZ = 8 / WC;
+    constexpr bool STEP = MODE != 1;  // MODE 0: step, 1: sums only, 2: step + energy partials
+    constexpr bool KEN = MODE == 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int b = blockIdx.x;
     const int zg = b % nzg;
@@ -117,7 +123,10 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
     const int ch = b / nct;
     const int zl = zl_begin + zg * WZ + warp / WC;
     const int segk = ct * WC + warp % WC;
-    if (zl >= zl_end || segk >= nsegk) return;  // whole warp leaves; no block-level sync below
+    if (zl >= zl_end || segk >= nsegk) {  // whole warp leaves; no block-level sync below
+        if (KEN && lane == 0) pen[(size_t)blockIdx.x * 8 + warp] = 0.0;
+        return;
+    }
 
     const int S = P.S;
     const int c0 = (segk * 32 + lane) * CPL;
@@ -140,7 +149,7 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
             CC[j][q] = 0.0;
             cacc[j][q] = 0.0;
         }
-    if (MODE == 0) {
+    if (STEP) {
 #pragma unroll
         for (int j = 0; j < CPL; ++j)
             if (valid[j]) {
@@ -152,13 +161,14 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
             }
     }
 
+    double eacc = 0.0;  // energy partial of this lane (MODE 2)
     const int r_begin = ch * rchunk;
     const int r_end = min(S, r_begin + rchunk);
     const int tab0 = c0 / kTabSeg;  // all CPL cells of a lane share a table segment (CPL | 64)
 
     // L2 prefetch `pf_rows` rows ahead (one request per 128-byte line): turns the HBM latency of the
     // streamed rows into an L2 hit without spending registers on software pipelining.
-    const bool pf_lane = MODE == 0 && pf_rows > 0 && valid[0] && ((lane * CPL) & 3) == 0;
+    const bool pf_lane = STEP && pf_rows > 0 && valid[0] && ((lane * CPL) & 3) == 0;
     if (pf_lane) {
         for (int r = r_begin; r < min(r_end, r_begin + pf_rows); ++r) {
             const size_t o = zbase + ((size_t)r * S + c0) * 4;
@@ -179,18 +189,18 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
         for (int j = 0; j < CPL; ++j) {
             if (valid[j]) {
                 ld256_nc(u + rowoff + j * 4, uq[j]);
-                if (MODE == 0) ld256_cs(w + rowoff + j * 4, upq[j]);
+                if (STEP) ld256_cs(w + rowoff + j * 4, upq[j]);
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { uq[j][q] = 0.0; upq[j][q] = 0.0; }
             }
-            if (MODE != 0) {
+            if (!STEP) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) upq[j][q] = 0.0;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) { zm[j][q] = 0.0; zp[j][q] = 0.0; }
-            if (MODE == 0 && K3D && valid[j]) {
+            if (STEP && K3D && valid[j]) {
                 if (zm_on) ld256_nc(u + rowoff - plane + j * 4, zm[j]);
                 if (zp_on) ld256_nc(u + rowoff + plane + j * 4, zp[j]);
             }
@@ -200,7 +210,7 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
         const bool all_plain = __all_sync(0xffffffffu, det < 0);
 
         double RS[4] = {0, 0, 0, 0}, RC[4] = {0, 0, 0, 0};
-        if (MODE == 0) {
+        if (STEP) {
             const double2 *ri = reinterpret_cast<const double2 *>(P.rowinfo + ((size_t)zl * S + r) * 8);
             const double2 a = ri[0], bb = ri[1], c = ri[2], d = ri[3];
             RS[0] = a.x; RS[1] = a.y; RS[2] = bb.x; RS[3] = bb.y;
@@ -227,6 +237,10 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
                     un[q] = 2.0 * uq[j][q] - upq[j][q] + coeff * lap -
                             damping * (uq[j][q] - upq[j][q]);
                     pun[q] = valid[j] ? un[q] : 0.0;
+                    if (KEN && valid[j]) {
+                        const double dv = un[q] - uq[j][q];
+                        eacc += dv * dv * inv_coeff - un[q] * lap;
+                    }
                 }
             } else {
                 unsigned f = fplain;
@@ -239,11 +253,12 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
                     io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[j][q]; io.CC[q] = CC[j][q];
                 }
                 cell_update_detail(P, u, det, (c0 + j) & (kTabSeg - 1), (long long)(rowoff + j * 4), f,
-                                   coeff, damping, io);
+                                   coeff, damping, inv_coeff, io);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { un[q] = io.un[q]; pun[q] = io.pun[q]; }
+                if (KEN) eacc += io.e;
             }
-            if (MODE == 0 && valid[j]) st256_cs(w + rowoff + j * 4, un);
+            if (STEP && valid[j]) st256_cs(w + rowoff + j * 4, un);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 cacc[j][q] += pun[q];
@@ -255,6 +270,10 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
 #pragma unroll
     for (int j = 0; j < CPL; ++j)
         if (valid[j]) st256(pcol + (((size_t)zl * nchunk + ch) * S + (c0 + j)) * 4, cacc[j]);
+    if (KEN) {
+        eacc = warp_sum(eacc);
+        if (lane == 0) pen[(size_t)blockIdx.x * 8 + warp] = eacc;
+    }
 }
 
 // 3-D step with explicit on-chip sharing of the z neighbours (cp.async multi-stage pipeline).
@@ -404,7 +423,7 @@ lat_step3d_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u
                     io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[q]; io.CC[q] = CC[q];
                 }
                 cell_update_detail(P, u, det, c & (kTabSeg - 1),
-                                   (long long)(zbase + ((size_t)r * S + c) * 4), f, coeff, damping, io);
+                                   (long long)(zbase + ((size_t)r * S + c) * 4), f, coeff, damping, 0.0, io);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { un[q] = io.un[q]; pun[q] = io.pun[q]; }
             }
@@ -432,10 +451,25 @@ lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, int nrowblk,
                     const double *__restrict__ prow, const double *__restrict__ pcol,
                     double *__restrict__ rowinfo, double *__restrict__ colinfo,
                     const double *__restrict__ state, const long long *__restrict__ probe_idx,
-                    int n_probes, double *__restrict__ probe_row)
+                    int n_probes, double *__restrict__ probe_row, const double *__restrict__ pen,
+                    long long n_pen, double *__restrict__ energy_out)
 {
     if (blockIdx.x == 0)
         for (int t = threadIdx.x; t < n_probes; t += blockDim.x) probe_row[t] = state[probe_idx[t]];
+    if (blockIdx.x == gridDim.x - 1 && energy_out != nullptr) {
+        // last CTA: staggered energy E_{t+1/2} = 1/2 * sum of the per-warp partials, fixed order
+        __shared__ double red[256];
+        double a = 0.0;
+        for (long long i = threadIdx.x; i < n_pen; i += 256) a += pen[i];
+        red[threadIdx.x] = a;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) *energy_out = 0.5 * red[0];
+        return;
+    }
     const long long nline = (long long)Lloc * S;
     if ((int)blockIdx.x < nrowblk) {
         const int lane = threadIdx.x & 31;

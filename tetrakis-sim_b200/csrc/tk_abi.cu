@@ -116,6 +116,13 @@ struct tk_plan {
     int cpl = 2, wc = 8, rchunk = 64, nchunk = 1, nsegk = 1;
     int wz3d = 0, stages3d = 0, minb3d = 2;  // wz3d > 0: 3-D steps use lat_step3d_kernel<wz3d, stages3d, minb3d>
     int pf_rows = 0;                         // register path: L2 prefetch distance in rows (0 = off)
+    // energy series (optional): per-warp / per-CTA partials + one value per step
+    double *pen = nullptr;
+    long long pen_cap = 0, pen_used = 0;
+    double *energy_series = nullptr;
+    long long energy_cap = 0, energy_row = 0;
+    bool energy_on = false;
+    cudaStream_t launch_stream = nullptr;    // stream of the next layer launch (defaults to `stream`)
     int minb = 1;                            // register path: min resident CTAs per SM asked of ptxas
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
@@ -170,9 +177,17 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
     const long long grid = (long long)p->nchunk * nct * nzg;
     if (grid <= 0) return TK_OK;
     if (grid > 0x7fffffffLL) return fail(TK_ERR_INVALID, "lattice grid too large");
-    tk::lat_step_kernel<CPL, WC, K3D, MODE, MINB><<<(unsigned)grid, 256, 0, p->stream>>>(
+    double *pen = nullptr;
+    if (MODE == 2) {
+        if (p->pen_used + grid * 8 > p->pen_cap) return fail(TK_ERR_INVALID, "energy partial buffer overflow");
+        pen = p->pen + p->pen_used;
+        p->pen_used += grid * 8;
+    }
+    cudaStream_t st = p->launch_stream ? p->launch_stream : p->stream;
+    tk::lat_step_kernel<CPL, WC, K3D, MODE, MINB><<<(unsigned)grid, 256, 0, st>>>(
         p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
-        zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg, p->pf_rows);
+        zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg, p->pf_rows, pen,
+        p->coeff > 0.0 ? 1.0 / p->coeff : 0.0);
     p->launches++;
     TK_CUDA(cudaGetLastError());
     return TK_OK;
@@ -195,6 +210,13 @@ template <int MODE>
 int launch_lat_dispatch(tk_plan *p, int zl_begin, int zl_end)
 {
     const bool k3d = p->lat.halo != 0;
+    if (MODE == 2) {  // step + energy partials: instantiated for the default shapes only
+        if (p->cpl == 1 && p->wc == 8)
+            return k3d ? launch_lat<1, 8, true, 2, 2>(p, zl_begin, zl_end) : launch_lat<1, 8, false, 2, 3>(p, zl_begin, zl_end);
+        if (p->cpl == 1 && p->wc == 1)
+            return k3d ? launch_lat<1, 1, true, 2, 2>(p, zl_begin, zl_end) : launch_lat<1, 1, false, 2, 3>(p, zl_begin, zl_end);
+        return fail(TK_ERR_INVALID, "the energy series needs the default kernel tiling (cpl=1, wc=1 or 8)");
+    }
     if (MODE != 0) {  // sums-only pass: register pressure is irrelevant, one instantiation per shape
 #define X(CPL, WC, MB)                                                        \
     if (p->cpl == CPL && p->wc == WC && p->minb == MB)                        \
@@ -310,11 +332,42 @@ int lat_finalise(tk_plan *p, const double *state, double *probe_row)
     const long long nline = (long long)p->lat.Lloc * p->lat.S;
     const int nrowblk = (int)((nline + 7) / 8);
     const int ncolblk = (int)((nline * 4 + 31) / 32);
-    tk::lat_finalise_kernel<<<(unsigned)(nrowblk + ncolblk), 256, 0, p->stream>>>(
+    double *eout = nullptr;
+    if (p->energy_on && p->pen_used > 0 && p->energy_row < p->energy_cap)
+        eout = p->energy_series + p->energy_row++;
+    tk::lat_finalise_kernel<<<(unsigned)(nrowblk + ncolblk + (eout ? 1 : 0)), 256, 0, p->stream>>>(
         p->lat.S, p->lat.Lloc, p->nsegk, p->nchunk, nrowblk, p->prow, p->pcol, p->rowinfo, p->colinfo,
-        state, p->probe_idx, probe_row ? p->n_probes : 0, probe_row);
+        state, p->probe_idx, probe_row ? p->n_probes : 0, probe_row, p->pen, p->pen_used, eout);
+    p->pen_used = 0;
     p->launches++;
     TK_CUDA(cudaGetLastError());
+    return TK_OK;
+}
+
+int set_energy(tk_plan *p, bool on, long long steps)
+{
+    p->energy_on = false;
+    p->energy_row = 0;
+    p->pen_used = 0;
+    if (p->energy_series) { cudaFree(p->energy_series); p->energy_series = nullptr; }
+    if (!on) return TK_OK;
+    long long need;
+    if (p->kind == kGraph) {
+        need = (p->n + 255) / 256;
+    } else {
+        TK_REQUIRE(p->wz3d == 0, "the energy series is not available with TK_LAT3D=1");
+        const int wz = 8 / p->wc;
+        need = (long long)p->nchunk * ((p->nsegk + p->wc - 1) / p->wc) * ((p->lat.Lloc + wz - 1) / wz + 2) * 8;
+    }
+    if (need > p->pen_cap) {
+        if (p->pen) cudaFree(p->pen);
+        p->pen = nullptr;
+        TK_CUDA(cudaMalloc((void **)&p->pen, std::max<long long>(need, 1) * sizeof(double)));
+        p->pen_cap = need;
+    }
+    TK_CUDA(cudaMalloc((void **)&p->energy_series, std::max<long long>(steps, 1) * sizeof(double)));
+    p->energy_cap = steps;
+    p->energy_on = true;
     return TK_OK;
 }
 
@@ -349,10 +402,19 @@ int graph_step(tk_plan *p, double coeff, double damping)
 {
     const unsigned grid = (unsigned)((p->n + 255) / 256);
     if (grid) {
-        tk::graph_step_kernel<<<grid, 256, 0, p->stream>>>(p->n, p->slice_off, p->ell_idx, p->deg,
-                                                          p->inv_mass, p->potential, p->buf[p->cur],
-                                                          p->buf[p->cur ^ 1], coeff, damping);
-        p->launches++;
+        const double inv_coeff = coeff > 0.0 ? 1.0 / coeff : 0.0;
+        if (p->energy_on && p->energy_row < p->energy_cap) {
+            tk::graph_step_kernel<true><<<grid, 256, 0, p->stream>>>(
+                p->n, p->slice_off, p->ell_idx, p->deg, p->inv_mass, p->potential, p->buf[p->cur],
+                p->buf[p->cur ^ 1], coeff, damping, p->pen, inv_coeff);
+            tk::energy_reduce_kernel<<<1, 256, 0, p->stream>>>(p->pen, grid, p->energy_series + p->energy_row++);
+            p->launches += 2;
+        } else {
+            tk::graph_step_kernel<false><<<grid, 256, 0, p->stream>>>(
+                p->n, p->slice_off, p->ell_idx, p->deg, p->inv_mass, p->potential, p->buf[p->cur],
+                p->buf[p->cur ^ 1], coeff, damping, nullptr, inv_coeff);
+            p->launches++;
+        }
         TK_CUDA(cudaGetLastError());
     }
     p->cur ^= 1;
@@ -862,7 +924,18 @@ int tk_lattice_step_layers(tk_plan *p, int32_t zl_begin, int32_t zl_end)
     TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
     TK_REQUIRE(0 <= zl_begin && zl_begin <= zl_end && zl_end <= p->lat.Lloc, "bad layer range");
     if (p->wz3d) return launch_lat3d_dispatch(p, zl_begin, zl_end);
+    if (p->energy_on) return launch_lat_dispatch<2>(p, zl_begin, zl_end);
     return launch_lat_dispatch<0>(p, zl_begin, zl_end);
+}
+
+int tk_lattice_step_layers_on(tk_plan *p, int32_t zl_begin, int32_t zl_end, void *cuda_stream)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    TK_REQUIRE(p->wz3d == 0, "side-stream launches are not available with TK_LAT3D=1");
+    p->launch_stream = (cudaStream_t)cuda_stream;
+    const int rc = tk_lattice_step_layers(p, zl_begin, zl_end);
+    p->launch_stream = nullptr;
+    return rc;
 }
 
 int tk_lattice_step_end(tk_plan *p)
@@ -877,9 +950,10 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     TK_REQUIRE(p && a, "NULL argument");
     TK_REQUIRE(a->steps >= 0, "steps must be >= 0");
     TK_REQUIRE(a->n_probes == 0 || (a->probe_index && a->probe_out), "probe arrays NULL");
-    TK_REQUIRE(a->energy_out == nullptr, "energy series not implemented in this ABI version");
     TK_CUDA(cudaSetDevice(p->device));
     int rc = set_probes(p, a->n_probes, a->probe_index, a->steps + 1);
+    if (rc) return rc;
+    rc = set_energy(p, a->energy_out != nullptr && a->steps > 0, a->steps);
     if (rc) return rc;
 
     // optional full history (physics.py:104,129), staged through a bounded device buffer
@@ -964,6 +1038,9 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     if (d_hist && hist_fill > 0)
         TK_RUN_CUDA(cudaMemcpyAsync(a->history_out + (size_t)hist_done * p->n, d_hist,
                                     (size_t)hist_fill * row_bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (p->energy_on)
+        TK_RUN_CUDA(cudaMemcpyAsync(a->energy_out, p->energy_series, (size_t)a->steps * sizeof(double),
+                                    cudaMemcpyDeviceToHost, p->stream));
     if (p->n_probes > 0)
         TK_RUN_CUDA(cudaMemcpyAsync(a->probe_out, p->probe_series,
                                     (size_t)(a->steps + 1) * p->n_probes * sizeof(double),
@@ -989,6 +1066,7 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
         for (auto &e : kev) cudaEventDestroy(e);
     }
     if (d_hist) cudaFree(d_hist);
+    p->energy_on = false;
     return TK_OK;
 #undef TK_RUN_TRY
 #undef TK_RUN_CUDA
@@ -1020,6 +1098,8 @@ int tk_plan_destroy(tk_plan *p)
     for (void *q : p->owned) cudaFree(q);
     if (p->probe_idx) cudaFree(p->probe_idx);
     if (p->probe_series) cudaFree(p->probe_series);
+    if (p->pen) cudaFree(p->pen);
+    if (p->energy_series) cudaFree(p->energy_series);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return TK_OK;

@@ -14,6 +14,9 @@ Extra keyword-only arguments (all optional; the positional signature is the refe
   record   "all" (default for graphs: every state, as the reference returns) or "probes"
            (default for a LatticeSpec: only the probe nodes' time series and the final state).
   probes   nodes to record when record="probes" (default: the kicked nodes)
+  energy   also return ``history.energy``: the staggered discrete energy between consecutive states,
+           ``steps`` values, conserved to rounding when damping == 0 (a new diagnostic; the reference
+           computes no energy -- SURVEY.md section 2)
 """
 
 from __future__ import annotations
@@ -52,6 +55,7 @@ class SimulationHistory(list):
         self.probe_series: np.ndarray | None = None  # (steps+1, n_probes)
         self.final_state: np.ndarray | None = None
         self.elapsed_ms: float | None = None
+        self.energy: np.ndarray | None = None  # (steps,) staggered energy, when energy=True
         self._index: dict | None = None  # node -> column of ``array``
 
 
@@ -120,7 +124,7 @@ def _cfl(max_degree: int, c: float, dt: float, steps: int, damping: float):
     return effective_dt, metadata
 
 
-def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes):
+def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes, energy):
     comp: CompiledGraph
     if path == "structured":
         comp = structured_from_graph(G, device=device)
@@ -143,7 +147,7 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
         coeff = (c * effective_dt) ** 2  # physics.py:105
         n = len(nodes)
         if record == "all":
-            out = comp.plan.run(steps, coeff, damping, history=True, timed=True)
+            out = comp.plan.run(steps, coeff, damping, history=True, timed=True, energy=energy)
             arr = out["history"]
             if comp.state_index is not None:
                 arr = np.ascontiguousarray(arr[:, comp.state_index])
@@ -160,7 +164,7 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
         else:
             pnodes = list(probes) if probes is not None else list(kicks)
             pidx = [to_state(index[p]) for p in pnodes]
-            out = comp.plan.run(steps, coeff, damping, probes=pidx, timed=True)
+            out = comp.plan.run(steps, coeff, damping, probes=pidx, timed=True, energy=energy)
             series = out["probes"] if pidx else np.empty((steps + 1, 0))
             states = [dict(zip(pnodes, row)) for row in series.tolist()]
             hist = SimulationHistory(states, dt=effective_dt, wave_speed=c, metadata=metadata)
@@ -168,12 +172,13 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
             fin = comp.plan.get_state()
             hist.final_state = fin if comp.state_index is None else fin[comp.state_index]
         hist.elapsed_ms = out["elapsed_ms"]
+        hist.energy = None if out["energy"] is None else out["energy"] * (c * c)
         return hist
     finally:
         comp.plan.close()
 
 
-def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device, record, probes):
+def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device, record, probes, energy):
     plan = compile_lattice(spec, device=device)
     try:
         effective_dt, metadata = _cfl(plan.max_degree, c, dt, steps, damping)
@@ -186,9 +191,9 @@ def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device,
         pnodes = list(probes) if probes is not None else list(kicks)
         pidx = [spec.index(p) for p in pnodes]
         if record == "all":
-            out = plan.run(steps, coeff, damping, probes=pidx, history=True, timed=True)
+            out = plan.run(steps, coeff, damping, probes=pidx, history=True, timed=True, energy=energy)
         else:
-            out = plan.run(steps, coeff, damping, probes=pidx, timed=True)
+            out = plan.run(steps, coeff, damping, probes=pidx, timed=True, energy=energy)
         series = out["probes"] if pidx else np.empty((steps + 1, 0))
         states = [dict(zip(pnodes, row)) for row in series.tolist()]
         hist = SimulationHistory(states, dt=effective_dt, wave_speed=c, metadata=metadata)
@@ -196,6 +201,7 @@ def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device,
         hist.array = out["history"]  # (steps+1, num_slots) in device layout when record="all"
         hist.final_state = hist.array[-1] if hist.array is not None else plan.get_state()
         hist.elapsed_ms = out["elapsed_ms"]
+        hist.energy = None if out["energy"] is None else out["energy"] * (c * c)
         hist.metadata["launches"] = plan.launches
         return hist
     finally:
@@ -214,6 +220,7 @@ def run_wave_sim(
     path: str = "auto",
     record: str | None = None,
     probes: list | None = None,
+    energy: bool = False,
 ) -> SimulationHistory:
     """Simulate the discrete wave equation on ``G`` (reference physics.py:41-131).
 
@@ -226,8 +233,8 @@ def run_wave_sim(
     if path not in ("auto", "graph", "structured"):
         raise ValueError("path must be 'auto', 'graph' or 'structured'")
     if isinstance(G, LatticeSpec):
-        return _run_lattice(G, steps, initial_data, c, dt, damping, device, record or "probes", probes)
-    return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes)
+        return _run_lattice(G, steps, initial_data, c, dt, damping, device, record or "probes", probes, energy)
+    return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes, energy)
 
 
 def run_fft(

@@ -126,9 +126,17 @@ class SlabRunner:
         """Row/column sums of the initial state + first halo fill."""
         self.backend.step_begin(coeff, damping)
         self._pending = self._post(next_state=False)
-        self._wait()
+        if self.comm_stream is not None:
+            import torch
+
+            self._ev_end = torch.cuda.Event()
+            self._ev_end.record(self.main_stream)
+        else:
+            self._wait()
 
     def step(self):
+        if self.comm_stream is not None:
+            return self._step_cuda()
         L = self.n_local_layers
         b = self.backend
         self._wait()  # halos of u_t are in place
@@ -140,8 +148,49 @@ class SlabRunner:
             b.step_layers(1, L - 1)  # ... while the interior is updated
         b.step_end()
 
+    def _step_cuda(self):
+        """Boundary layers + halo exchange on the (high-priority) side stream, concurrently with the
+        interior layers on the main stream; the finalise/swap joins both.
+
+        The two boundary launches are small (one layer each: a few warps per SM, latency-bound, ~0.1
+        ms) -- run back to back with the interior they cost 0.4 ms per step (measured at N=2); run
+        beside it they are free and the NCCL transfer starts ~0.8 ms before it is needed."""
+        import torch
+
+        L, b = self.n_local_layers, self.backend
+        side, main = self.comm_stream, self.main_stream
+        side.wait_event(self._ev_end)  # row/column sums of u_t (previous finalise) are ready
+        with torch.cuda.stream(side):
+            self._wait()  # halos of u_t have arrived (orders the side stream after NCCL)
+            b.step_layers_on(0, 1, side.cuda_stream)
+            if L > 1:
+                b.step_layers_on(L - 1, L, side.cuda_stream)
+            ev_bnd = torch.cuda.Event()
+            ev_bnd.record(side)
+            self._pending = self._post_current_stream(next_state=True)
+        if L > 2:
+            b.step_layers(1, L - 1)
+        main.wait_event(ev_bnd)
+        b.step_end()
+        self._ev_end = torch.cuda.Event()
+        self._ev_end.record(main)
+
+    def _post_current_stream(self, next_state: bool):
+        if self.world == 1 or self.dist is None:
+            return []
+        d = self.dist
+        pl = self.backend.planes(next_state)
+        ops = []
+        if self.lo is not None:
+            ops += [d.P2POp(d.isend, pl["send_lo"], self.lo), d.P2POp(d.irecv, pl["recv_lo"], self.lo)]
+        if self.hi is not None:
+            ops += [d.P2POp(d.isend, pl["send_hi"], self.hi), d.P2POp(d.irecv, pl["recv_hi"], self.hi)]
+        return d.batch_isend_irecv(ops) if ops else []
+
     def finish(self):
         self._wait()
+        if self.comm_stream is not None:
+            self.main_stream.wait_stream(self.comm_stream)
 
 
 def global_max_degree(plan_max: int, dist, device=None) -> int:
@@ -177,7 +226,7 @@ def bench_slabs(args) -> int:
     spec = LatticeSpec(size=size, dim=3, layers=per_gpu * world, defect="blackhole", radius=64.0)
 
     main = torch.cuda.current_stream(dev)
-    comm = torch.cuda.Stream(dev)
+    comm = torch.cuda.Stream(dev, priority=-1)  # boundary layers + NCCL: scheduled ahead of the interior
     backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=local)
     runner = SlabRunner(spec, backend, rank, world, dist, comm_stream=comm, main_stream=main)
     maxdeg = global_max_degree(backend.max_degree, dist, dev)

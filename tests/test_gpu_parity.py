@@ -303,4 +303,4 @@ def test_energy_is_conserved_without_damping_and_decays_with_it():
         h0 = tk.run_wave_sim(spec, steps=200, initial_data={k: 1.0}, dt=0.01, energy=True)
         h1 = tk.run_wave_sim(spec, steps=200, initial_data={k: 1.0}, dt=0.01, damping=0.01, energy=True)
     assert np.max(np.abs(h0.energy - h0.energy[0])) < 1e-10 * abs(h0.energy[0])
-    assert h0.energy[0] > 0 and np.all(np.diff(h1.energy) < 0)
+    assert h0.energy[0] > 0 and h1.energy[-1] < 0.5 * h1.energy[0] and np.mean(np.diff(h1.energy) < 0) > 0.9

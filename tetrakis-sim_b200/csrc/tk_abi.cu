@@ -924,8 +924,16 @@ int tk_lattice_step_layers(tk_plan *p, int32_t zl_begin, int32_t zl_end)
     TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
     TK_REQUIRE(0 <= zl_begin && zl_begin <= zl_end && zl_end <= p->lat.Lloc, "bad layer range");
     if (p->wz3d) return launch_lat3d_dispatch(p, zl_begin, zl_end);
-    if (p->energy_on) return launch_lat_dispatch<2>(p, zl_begin, zl_end);
-    return launch_lat_dispatch<0>(p, zl_begin, zl_end);
+    // A thin launch (the one-layer boundary launches of a slab run) with the 8-layers-per-CTA shape
+    // would leave 7 of 8 warps of every CTA idle while still occupying its slot; use the
+    // 8-segments-per-CTA shape for it (same partial-sum layout, so launches can be mixed in a step).
+    const int wc_saved = p->wc;
+    if (p->lat.halo && p->cpl == 1 && p->wc == 1 && zl_end - zl_begin <= 2 && lat_supported(1, 8, p->minb))
+        p->wc = 8;
+    const int rc = p->energy_on ? launch_lat_dispatch<2>(p, zl_begin, zl_end)
+                                : launch_lat_dispatch<0>(p, zl_begin, zl_end);
+    p->wc = wc_saved;
+    return rc;
 }
 
 int tk_lattice_step_layers_on(tk_plan *p, int32_t zl_begin, int32_t zl_end, void *cuda_stream)

@@ -228,7 +228,9 @@ def bench_slabs(args) -> int:
     main = torch.cuda.current_stream(dev)
     comm = torch.cuda.Stream(dev, priority=-1)  # boundary layers + NCCL: scheduled ahead of the interior
     backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=local)
-    runner = SlabRunner(spec, backend, rank, world, dist, comm_stream=comm, main_stream=main)
+    mode = os.environ.get("TK_SLAB_MODE", "full")  # diagnostics: "nocomm" skips the exchange, "serial"
+    runner = SlabRunner(spec, backend, rank, world, None if mode == "nocomm" else dist,
+                        comm_stream=None if mode == "serial" else comm, main_stream=main)
     maxdeg = global_max_degree(backend.max_degree, dist, dev)
     dt_eff = min(0.1, 1.0 / np.sqrt(maxdeg))
     coeff = dt_eff**2
@@ -254,11 +256,13 @@ def bench_slabs(args) -> int:
         torch.cuda.synchronize()
         dist.barrier()
         e0.record(main)
+        h0 = time.perf_counter()
         runner.begin(coeff, 0.0)
         for _ in range(args.steps):
             runner.step()
         runner.finish()
         e1.record(main)
+        host_enqueue_s = time.perf_counter() - h0
         torch.cuda.synchronize()
         dist.barrier()
     launches = backend.launches - l0
@@ -320,6 +324,7 @@ def bench_slabs(args) -> int:
                     "h2d_bytes_per_step": 16.0 / args.steps,
                     "d2h_bytes_per_step": world * final.nbytes / args.steps, "seconds": e2e_s},
             "gpu_launches": launches, "clocks": clk.summary(),
+            "host_enqueue_ms_per_step": 1e3 * host_enqueue_s / args.steps, "slab_mode": mode,
             "checksum_sum_u": float(cs.item()), "checksum_expected": float(args.warmup + args.steps + 1),
         }
         print(json.dumps(line), flush=True)

@@ -297,6 +297,7 @@ def bench_slabs(args) -> int:
     backend.set_state_sparse(*kicks)
     o = backend.plan.run(min(args.steps, 50), coeff, 0.0, timed=True)
     kms = o["step_kernel_ms"] / min(args.steps, 50)
+    alone_ms = o["elapsed_ms"] / min(args.steps, 50)  # this rank's slab stepped alone: step + finalise
     local_nodes = backend.num_nodes  # slots; the black hole removes < 1 %
     from bench import BYTES_PER_UPDATE, METRIC, UNIT, measured_peak_gbs
 
@@ -325,6 +326,10 @@ def bench_slabs(args) -> int:
                     "d2h_bytes_per_step": world * final.nbytes / args.steps, "seconds": e2e_s},
             "gpu_launches": launches, "clocks": clk.summary(),
             "host_enqueue_ms_per_step": 1e3 * host_enqueue_s / args.steps, "slab_mode": mode,
+            # the same 64-layer slab on one GPU with no neighbours (rank 0, measured in this run): the
+            # denominator for weak scaling of THIS workload (bench.py --gpus 1 defaults to the 2-D cfg2)
+            "single_gpu_same_workload": {"value": local_nodes / (alone_ms * 1e-3) / 1e9, "unit": UNIT,
+                                         "ms_per_step": alone_ms},
             "checksum_sum_u": float(cs.item()), "checksum_expected": float(args.warmup + args.steps + 1),
         }
         print(json.dumps(line), flush=True)

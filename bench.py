@@ -44,6 +44,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[workload]["bytes"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
 
@@ -267,7 +276,8 @@ def gpu_single(args):
                    "l2": f"state {2 * spec.num_slots * 8 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
                    "tiling": tiling},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(workload), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": n_updates * BYTES_PER_UPDATE,
                      "kernel": "lat_step_kernel", "bytes_per_update": BYTES_PER_UPDATE,
                      "kernel_ms_per_launch": kms / args.steps,
                      "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0},

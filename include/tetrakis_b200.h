@@ -153,6 +153,32 @@ int tk_lattice_step_layers_on(tk_plan *plan, int32_t zl_begin, int32_t zl_end, v
 /* After every layer was updated: finish the row/column sums of the new state, swap buffers. */
 int tk_lattice_step_end(tk_plan *plan);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused halo push over NVLink peer memory (one process per GPU).
+ * Each rank exports its two state buffers with cudaIpc (tk_lattice_ipc_export: 2 x 64-byte handles),
+ * ships the handles to its z-neighbours (torch.distributed object gather), maps theirs
+ * (tk_ipc_open) and attaches them (tk_lattice_peer_attach).  From then on the step kernel stores the
+ * first / last owned layer of u_{t+1} into the neighbour's halo plane as it computes it, and the only
+ * per-step synchronisation is a pair of stream-ordered 64-bit flags (cuStreamWriteValue64 /
+ * cuStreamWaitValue64, no kernel spins): tk_lattice_signal(v) after the boundary launch,
+ * tk_lattice_wait(v) before the next one.  side: 0 = lower neighbour (rank-1), 1 = upper.
+ * ------------------------------------------------------------------------------------------ */
+int tk_lattice_ipc_export(tk_plan *plan, void *handles_2x64);
+int tk_ipc_open(int device, const void *handle_64, void **dev_ptr);
+int tk_ipc_close(int device, void *dev_ptr);
+/* peer_buf0/1: the neighbour's two state buffers (device pointers valid in this process);
+ * peer_layers: number of layers the neighbour owns.  Pass NULL pointers to detach that side. */
+int tk_lattice_peer_attach(tk_plan *plan, int32_t side, void *peer_buf0, void *peer_buf1,
+                           int32_t peer_layers);
+/* Copy the boundary planes of the CURRENT state into the attached neighbours' halos (initial fill). */
+int tk_lattice_push_halos(tk_plan *plan, void *cuda_stream);
+/* Stream-ordered: write `value` into both attached neighbours' arrival flags / wait until both of
+ * this rank's arrival flags are >= value. */
+int tk_lattice_signal(tk_plan *plan, uint64_t value, void *cuda_stream);
+int tk_lattice_wait(tk_plan *plan, uint64_t value, void *cuda_stream);
+/* Device addresses of this plan's two state buffers (for attaching plans of the same process). */
+int tk_lattice_state_ptrs(tk_plan *plan, void **buf0, void **buf1);
+
 /* Tiling the lattice step kernel uses (diagnostics for bench.py): cells per lane, segments per
  * CTA, rows per CTA, resident CTAs per SM.  Overridable with TK_LAT_CPL / TK_LAT_WC / TK_LAT_RCHUNK. */
 int tk_lattice_tiling(const tk_plan *plan, int32_t *cells_per_lane, int32_t *segs_per_cta,

@@ -17,7 +17,7 @@ SPEC = dict(size=48, dim=3, layers=13, defect="blackhole", radius=4.2)
 STEPS, COEFF, DAMPING = 25, 0.003, 0.005
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, transport):
     import torch
     import torch.distributed as dist
 
@@ -32,7 +32,7 @@ def _worker(rank, world, port, out):
         backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=rank)
         runner = SlabRunner(spec, backend, rank, world, dist,
                             comm_stream=torch.cuda.Stream(dev, priority=-1),
-                            main_stream=torch.cuda.current_stream(dev))
+                            main_stream=torch.cuda.current_stream(dev), transport=transport)
         md = global_max_degree(backend.max_degree, dist, dev)
         kicks = {spec.index(spec.kick_node()): 1.0, spec.index((0, 0, 0, "B")): -0.5,
                  spec.index((spec.size - 1, 1, spec.layers - 1, "D")): 0.25}
@@ -46,13 +46,17 @@ def _worker(rank, world, port, out):
         np.save(os.path.join(out, f"slab{rank}.npy"), backend.get_state())
         if rank == 0:
             np.save(os.path.join(out, "maxdeg.npy"), np.array([md]))
+        dist.barrier()
+        if transport == "p2p":
+            backend.detach_peers()
         backend.plan.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_nccl_slab_run_matches_the_oracle(world, tmp_path):
+def test_multi_gpu_slab_run_matches_the_oracle(world, transport, tmp_path):
     import torch
     import torch.multiprocessing as mp
 
@@ -61,7 +65,7 @@ def test_nccl_slab_run_matches_the_oracle(world, tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), transport), nprocs=world, join=True)
     spec = tk.LatticeSpec(**SPEC)
     got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
     flags = np.full(spec.num_slots, 3, dtype=np.uint8)

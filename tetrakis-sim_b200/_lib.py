@@ -25,7 +25,9 @@ ABI_SYMBOLS = (
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
     "tk_plan_run", "tk_plan_launch_count", "tk_plan_destroy",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
-    "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling", "tk_dft_abs", "tk_ensemble_run",
+    "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
+    "tk_lattice_ipc_export", "tk_ipc_open", "tk_ipc_close", "tk_lattice_peer_attach",
+    "tk_lattice_push_halos", "tk_lattice_signal", "tk_lattice_wait", "tk_lattice_state_ptrs", "tk_dft_abs", "tk_ensemble_run",
 )  # fmt: skip
 
 
@@ -109,6 +111,14 @@ def lib():
     L.tk_lattice_step_layers.argtypes = [P, c_int32, c_int32]
     L.tk_lattice_step_layers_on.argtypes = [P, c_int32, c_int32, P]
     L.tk_lattice_step_end.argtypes = [P]
+    L.tk_lattice_ipc_export.argtypes = [P, P]
+    L.tk_ipc_open.argtypes = [c_int, P, POINTER(P)]
+    L.tk_ipc_close.argtypes = [c_int, P]
+    L.tk_lattice_peer_attach.argtypes = [P, c_int32, P, P, c_int32]
+    L.tk_lattice_push_halos.argtypes = [P, P]
+    L.tk_lattice_signal.argtypes = [P, ctypes.c_uint64, P]
+    L.tk_lattice_wait.argtypes = [P, ctypes.c_uint64, P]
+    L.tk_lattice_state_ptrs.argtypes = [P, POINTER(P), POINTER(P)]
     L.tk_lattice_tiling.argtypes = [P, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                                     POINTER(c_int32)]  # fmt: skip
     L.tk_dft_abs.argtypes = [c_int, P, c_int64, c_int64, P, P]
@@ -313,8 +323,42 @@ class Plan:
     def step_layers_on(self, zl_begin, zl_end, cuda_stream: int):
         check(lib().tk_lattice_step_layers_on(self._h, int(zl_begin), int(zl_end), c_void_p(cuda_stream)))
 
+    # -- fused halo push over peer memory ------------------------------------------------------
+    def ipc_export(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        check(lib().tk_lattice_ipc_export(self._h, buf))
+        return buf.raw
+
+    def state_ptrs(self):
+        a, b = c_void_p(), c_void_p()
+        check(lib().tk_lattice_state_ptrs(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def peer_attach(self, side: int, buf0, buf1, peer_layers: int):
+        check(lib().tk_lattice_peer_attach(self._h, int(side), c_void_p(buf0), c_void_p(buf1),
+                                           int(peer_layers)))
+
+    def push_halos(self, cuda_stream: int = 0):
+        check(lib().tk_lattice_push_halos(self._h, c_void_p(cuda_stream)))
+
+    def signal(self, value: int, cuda_stream: int = 0):
+        check(lib().tk_lattice_signal(self._h, int(value), c_void_p(cuda_stream)))
+
+    def wait(self, value: int, cuda_stream: int = 0):
+        check(lib().tk_lattice_wait(self._h, int(value), c_void_p(cuda_stream)))
+
     def step_end(self):
         check(lib().tk_lattice_step_end(self._h))
+
+
+def ipc_open(handle64: bytes, device: int = 0) -> int:
+    p = c_void_p()
+    check(lib().tk_ipc_open(device, ctypes.create_string_buffer(handle64, 64), ctypes.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr: int, device: int = 0) -> None:
+    check(lib().tk_ipc_close(device, c_void_p(ptr)))
 
 
 def dft_abs(series, device: int = 0):

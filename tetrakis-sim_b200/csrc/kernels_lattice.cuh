@@ -41,6 +41,11 @@ struct LatDev {
     const double *corr_sign;
     const double *rowinfo;  // [Lloc][S][8]: 0-3 RowSum(q) of the current state, 4-7 row participation count
     const double *colinfo;  // [Lloc][S][8]: same for columns
+    // Fused halo push (multi-GPU slabs): when set, the warps that update the first / last owned layer
+    // also store u_{t+1} straight into the z-neighbour's halo plane through an NVLink-mapped peer
+    // pointer (cudaIpc), so the boundary update and the halo exchange are one kernel.
+    double *peer_lo;        // lower neighbour's upper-halo plane of the buffer being written, or null
+    double *peer_hi;        // upper neighbour's lower-halo plane, or null
 };
 
 __device__ __forceinline__ unsigned plain_flags(const LatDev &P, int zl)
@@ -258,7 +263,13 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
                 for (int q = 0; q < 4; ++q) { un[q] = io.un[q]; pun[q] = io.pun[q]; }
                 if (KEN) eacc += io.e;
             }
-            if (STEP && valid[j]) st256_cs(w + rowoff + j * 4, un);
+            if (STEP && valid[j]) {
+                st256_cs(w + rowoff + j * 4, un);
+                if (K3D) {  // warp-uniform: zl is per warp
+                    if (zl == 0 && P.peer_lo) st256(P.peer_lo + (rowoff - zbase) + j * 4, un);
+                    if (zl == P.Lloc - 1 && P.peer_hi) st256(P.peer_hi + (rowoff - zbase) + j * 4, un);
+                }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 cacc[j][q] += pun[q];

@@ -123,6 +123,10 @@ struct tk_plan {
     long long energy_cap = 0, energy_row = 0;
     bool energy_on = false;
     cudaStream_t launch_stream = nullptr;    // stream of the next layer launch (defaults to `stream`)
+    // fused halo push: neighbours' state buffers (peer-mapped) and flag words
+    double *peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer]
+    int peer_layers[2] = {0, 0};
+    unsigned long long *flags = nullptr;     // this rank's arrival flags: [0] from below, [16] from above
     int minb = 1;                            // register path: min resident CTAs per SM asked of ptxas
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
@@ -184,6 +188,12 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
         p->pen_used += grid * 8;
     }
     cudaStream_t st = p->launch_stream ? p->launch_stream : p->stream;
+    if (K3D && MODE != 1) {
+        const size_t plane = (size_t)p->lat.S * p->lat.S * 4;
+        const int nb = p->cur ^ 1;  // every rank swaps in lockstep, so buffer parities agree
+        p->lat.peer_lo = p->peer_buf[0][nb] ? p->peer_buf[0][nb] + (size_t)(p->peer_layers[0] + 1) * plane : nullptr;
+        p->lat.peer_hi = p->peer_buf[1][nb] ? p->peer_buf[1][nb] : nullptr;
+    }
     tk::lat_step_kernel<CPL, WC, K3D, MODE, MINB><<<(unsigned)grid, 256, 0, st>>>(
         p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
         zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg, p->pf_rows, pen,
@@ -750,7 +760,8 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     TK_TRY(plan_upload(p, &p->colinfo, colinfo));
     TK_TRY(plan_alloc(p, &p->prow, (size_t)Lloc * S * nsegk_max * 4, true));
     TK_TRY(plan_alloc(p, &p->pcol, (size_t)Lloc * nchunk_alloc * S * 4, true));
-    TK_TRY(plan_alloc(p, &p->buf[0], (size_t)p->alloc, true));
+    TK_TRY(plan_alloc(p, &p->buf[0], (size_t)p->alloc + 32, true));  // + 256 B: halo arrival flags
+    p->flags = reinterpret_cast<unsigned long long *>(p->buf[0] + p->alloc);
     TK_TRY(plan_alloc(p, &p->buf[1], (size_t)p->alloc, true));
 
     tk::LatDev &P = p->lat;
@@ -1078,6 +1089,133 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     return TK_OK;
 #undef TK_RUN_TRY
 #undef TK_RUN_CUDA
+}
+
+// ---- fused halo push over peer memory
+namespace {
+typedef int (*stream_value64_fn)(void *stream, unsigned long long addr, unsigned long long value, unsigned int flags);
+stream_value64_fn g_write64 = nullptr, g_wait64 = nullptr;
+
+int load_stream_memops()
+{
+    if (g_write64 && g_wait64) return TK_OK;
+    cudaDriverEntryPointQueryResult q;
+    void *fw = nullptr, *fq = nullptr;
+    TK_CUDA(cudaGetDriverEntryPoint("cuStreamWriteValue64", &fw, cudaEnableDefault, &q));
+    TK_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue64", &fq, cudaEnableDefault, &q));
+    if (!fw || !fq) return fail(TK_ERR_CUDA, "driver has no 64-bit stream memory operations");
+    g_write64 = (stream_value64_fn)fw;
+    g_wait64 = (stream_value64_fn)fq;
+    return TK_OK;
+}
+}  // namespace
+
+int tk_lattice_ipc_export(tk_plan *p, void *handles)
+{
+    TK_REQUIRE(p && p->kind == kLattice && handles, "bad argument");
+    TK_CUDA(cudaSetDevice(p->device));
+    cudaIpcMemHandle_t h[2];
+    TK_CUDA(cudaIpcGetMemHandle(&h[0], p->buf[0]));
+    TK_CUDA(cudaIpcGetMemHandle(&h[1], p->buf[1]));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    memcpy(handles, h, 128);
+    return TK_OK;
+}
+
+int tk_ipc_open(int device, const void *handle, void **dev_ptr)
+{
+    TK_REQUIRE(handle && dev_ptr, "NULL argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    TK_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TK_OK;
+}
+
+int tk_ipc_close(int device, void *dev_ptr)
+{
+    int rc = check_device(device);
+    if (rc) return rc;
+    if (dev_ptr) TK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return TK_OK;
+}
+
+int tk_lattice_state_ptrs(tk_plan *p, void **buf0, void **buf1)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    if (buf0) *buf0 = p->buf[0];
+    if (buf1) *buf1 = p->buf[1];
+    return TK_OK;
+}
+
+int tk_lattice_peer_attach(tk_plan *p, int32_t side, void *b0, void *b1, int32_t peer_layers)
+{
+    TK_REQUIRE(p && p->kind == kLattice && p->lat.halo, "needs a 3-D lattice plan");
+    TK_REQUIRE(side == 0 || side == 1, "side must be 0 or 1");
+    TK_REQUIRE((b0 == nullptr) == (b1 == nullptr), "attach both buffers or none");
+    TK_REQUIRE(b0 == nullptr || peer_layers >= 1, "peer_layers must be >= 1");
+    TK_REQUIRE(p->wz3d == 0, "peer halo push is not available with TK_LAT3D=1");
+    p->peer_buf[side][0] = (double *)b0;
+    p->peer_buf[side][1] = (double *)b1;
+    p->peer_layers[side] = peer_layers;
+    return TK_OK;
+}
+
+int tk_lattice_push_halos(tk_plan *p, void *cuda_stream)
+{
+    TK_REQUIRE(p && p->kind == kLattice && p->lat.halo, "needs a 3-D lattice plan");
+    TK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : p->stream;
+    const size_t plane = (size_t)p->lat.S * p->lat.S * 4, bytes = plane * sizeof(double);
+    const int b = p->cur;
+    if (p->peer_buf[0][b])  // my first owned plane -> lower neighbour's upper halo
+        TK_CUDA(cudaMemcpyAsync(p->peer_buf[0][b] + (size_t)(p->peer_layers[0] + 1) * plane, p->buf[b] + plane,
+                                bytes, cudaMemcpyDeviceToDevice, st));
+    if (p->peer_buf[1][b])  // my last owned plane -> upper neighbour's lower halo
+        TK_CUDA(cudaMemcpyAsync(p->peer_buf[1][b], p->buf[b] + plane * p->lat.Lloc, bytes,
+                                cudaMemcpyDeviceToDevice, st));
+    return TK_OK;
+}
+
+int tk_lattice_signal(tk_plan *p, uint64_t value, void *cuda_stream)
+{
+    TK_REQUIRE(p && p->kind == kLattice && p->lat.halo, "needs a 3-D lattice plan");
+    TK_CUDA(cudaSetDevice(p->device));
+    int rc = load_stream_memops();
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : p->stream;
+    const size_t plane = (size_t)p->lat.S * p->lat.S * 4;
+    if (p->peer_buf[0][0]) {  // lower neighbour's "from above" flag: tail of its buffer 0, word 16
+        double *tail = p->peer_buf[0][0] + (size_t)(p->peer_layers[0] + 2) * plane;
+        const int e = g_write64(st, (unsigned long long)(reinterpret_cast<unsigned long long *>(tail) + 16), value, 0);
+        if (e) return fail(TK_ERR_CUDA, "cuStreamWriteValue64 failed with CUresult %d", e);
+    }
+    if (p->peer_buf[1][0]) {  // upper neighbour's "from below" flag: word 0
+        double *tail = p->peer_buf[1][0] + (size_t)(p->peer_layers[1] + 2) * plane;
+        const int e = g_write64(st, (unsigned long long)reinterpret_cast<unsigned long long *>(tail), value, 0);
+        if (e) return fail(TK_ERR_CUDA, "cuStreamWriteValue64 failed with CUresult %d", e);
+    }
+    return TK_OK;
+}
+
+int tk_lattice_wait(tk_plan *p, uint64_t value, void *cuda_stream)
+{
+    TK_REQUIRE(p && p->kind == kLattice && p->lat.halo, "needs a 3-D lattice plan");
+    TK_CUDA(cudaSetDevice(p->device));
+    int rc = load_stream_memops();
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : p->stream;
+    const unsigned int GEQ = 0x1;  // CU_STREAM_WAIT_VALUE_GEQ
+    if (p->peer_buf[0][0]) {
+        const int e = g_wait64(st, (unsigned long long)(p->flags), value, GEQ);
+        if (e) return fail(TK_ERR_CUDA, "cuStreamWaitValue64 failed with CUresult %d", e);
+    }
+    if (p->peer_buf[1][0]) {
+        const int e = g_wait64(st, (unsigned long long)(p->flags + 16), value, GEQ);
+        if (e) return fail(TK_ERR_CUDA, "cuStreamWaitValue64 failed with CUresult %d", e);
+    }
+    return TK_OK;
 }
 
 int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchunk, int32_t *occ)

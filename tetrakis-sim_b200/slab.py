@@ -61,6 +61,30 @@ class CudaSlabBackend:
             out[k] = self._views[key]
         return out
 
+    def attach_peers(self, dist, rank: int, world: int, spec: LatticeSpec):
+        """Map the z-neighbours' state buffers (cudaIpc) so the step kernel can push halos itself."""
+        from . import _lib
+
+        handles = [None] * world
+        dist.all_gather_object(handles, self.plan.ipc_export())
+        self._ipc = []
+        for side, nb in ((0, rank - 1), (1, rank + 1)):
+            if 0 <= nb < world:
+                b0 = _lib.ipc_open(handles[nb][:64], self.device)
+                b1 = _lib.ipc_open(handles[nb][64:], self.device)
+                self._ipc += [b0, b1]
+                zb, ze = spec.slab(nb, world)
+                self.plan.peer_attach(side, b0, b1, ze - zb)
+
+    def detach_peers(self):
+        from . import _lib
+
+        for side in (0, 1):
+            self.plan.peer_attach(side, None, None, 0)
+        for ptr in getattr(self, "_ipc", []):
+            _lib.ipc_close(ptr, self.device)
+        self._ipc = []
+
     def __getattr__(self, name):  # step_begin / step_layers / step_end / set_state_sparse / ...
         return getattr(self.plan, name)
 
@@ -69,7 +93,7 @@ class SlabRunner:
     """Steps one rank's slab and exchanges halos with the z-neighbours."""
 
     def __init__(self, spec: LatticeSpec, backend, rank: int, world: int, dist=None,
-                 comm_stream=None, main_stream=None):  # fmt: skip
+                 comm_stream=None, main_stream=None, transport: str = "nccl"):  # fmt: skip
         if spec.dim != 3:
             raise ValueError("slab sharding is for 3-D lattices (2-D sheets run as replicas)")
         if spec.layers < world:
@@ -81,6 +105,12 @@ class SlabRunner:
         self.hi = rank + 1 if rank < world - 1 else None
         self.comm_stream, self.main_stream = comm_stream, main_stream
         self._pending = []
+        # "nccl": send/recv of the boundary planes; "p2p": the step kernel stores them into the
+        # neighbours' halos through peer-mapped pointers, synchronised by stream-ordered flags
+        self.transport = transport if (dist is not None and world > 1 and comm_stream is not None) else "nccl"
+        self._push_count = 0
+        if self.transport == "p2p":
+            backend.attach_peers(dist, rank, world, spec)
 
     # -- index helpers --------------------------------------------------------------------------
     def owns(self, global_index: int) -> bool:
@@ -125,6 +155,19 @@ class SlabRunner:
     def begin(self, coeff: float, damping: float):
         """Row/column sums of the initial state + first halo fill."""
         self.backend.step_begin(coeff, damping)
+        if self.transport == "p2p":
+            import torch
+
+            ev = torch.cuda.Event()
+            ev.record(self.main_stream)
+            self.dist.barrier()  # nobody still reads the halos of a previous run
+            self.comm_stream.wait_event(ev)
+            self.backend.push_halos(self.comm_stream.cuda_stream)
+            self._push_count += 1
+            self.backend.signal(self._push_count, self.comm_stream.cuda_stream)
+            self._ev_end = torch.cuda.Event()
+            self._ev_end.record(self.main_stream)
+            return
         self._pending = self._post(next_state=False)
         if self.comm_stream is not None:
             import torch
@@ -135,6 +178,8 @@ class SlabRunner:
             self._wait()
 
     def step(self):
+        if self.transport == "p2p":
+            return self._step_p2p()
         if self.comm_stream is not None:
             return self._step_cuda()
         L = self.n_local_layers
@@ -168,6 +213,28 @@ class SlabRunner:
             ev_bnd = torch.cuda.Event()
             ev_bnd.record(side)
             self._pending = self._post_current_stream(next_state=True)
+        if L > 2:
+            b.step_layers(1, L - 1)
+        main.wait_event(ev_bnd)
+        b.step_end()
+        self._ev_end = torch.cuda.Event()
+        self._ev_end.record(main)
+
+    def _step_p2p(self):
+        """Fused boundary update + halo push: no NCCL in the loop.  Flag value k = "k pushes done"."""
+        import torch
+
+        L, b = self.n_local_layers, self.backend
+        side, main = self.comm_stream, self.main_stream
+        side.wait_event(self._ev_end)
+        b.wait(self._push_count, side.cuda_stream)  # the neighbours' planes of u_t sit in my halos
+        b.step_layers_on(0, 1, side.cuda_stream)  # ... and these launches push u_{t+1} into theirs
+        if L > 1:
+            b.step_layers_on(L - 1, L, side.cuda_stream)
+        ev_bnd = torch.cuda.Event()
+        ev_bnd.record(side)
+        self._push_count += 1
+        b.signal(self._push_count, side.cuda_stream)
         if L > 2:
             b.step_layers(1, L - 1)
         main.wait_event(ev_bnd)
@@ -229,8 +296,10 @@ def bench_slabs(args) -> int:
     comm = torch.cuda.Stream(dev, priority=-1)  # boundary layers + NCCL: scheduled ahead of the interior
     backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=local)
     mode = os.environ.get("TK_SLAB_MODE", "full")  # diagnostics: "nocomm" skips the exchange, "serial"
+    transport = os.environ.get("TK_SLAB_TRANSPORT", "p2p")
     runner = SlabRunner(spec, backend, rank, world, None if mode == "nocomm" else dist,
-                        comm_stream=None if mode == "serial" else comm, main_stream=main)
+                        comm_stream=None if mode == "serial" else comm, main_stream=main,
+                        transport=transport)
     maxdeg = global_max_degree(backend.max_degree, dist, dev)
     dt_eff = min(0.1, 1.0 / np.sqrt(maxdeg))
     coeff = dt_eff**2
@@ -299,7 +368,7 @@ def bench_slabs(args) -> int:
     kms = o["step_kernel_ms"] / min(args.steps, 50)
     alone_ms = o["elapsed_ms"] / min(args.steps, 50)  # this rank's slab stepped alone: step + finalise
     local_nodes = backend.num_nodes  # slots; the black hole removes < 1 %
-    from bench import BYTES_PER_UPDATE, METRIC, UNIT, measured_peak_gbs
+    from bench import BYTES_PER_UPDATE, METRIC, UNIT, measured_peak_gbs, ncu_traffic
 
     peak, peak_src = measured_peak_gbs()
     achieved = local_nodes * BYTES_PER_UPDATE / (kms * 1e-3) / 1e9
@@ -312,12 +381,17 @@ def bench_slabs(args) -> int:
                        "lattice": f"3-D tetrakis {size}x{size}x{spec.layers} ({per_gpu} layers per GPU), "
                                   f"black hole r=64 at the global centre, fp64",
                        "nodes": n_updates, "max_degree": maxdeg, "effective_dt": dt_eff,
-                       "parallelism": f"z-slabs x{world}, 1-plane halos, NCCL send/recv overlapped "
-                                      "with interior layers",
+                       "parallelism": (f"z-slabs x{world}, 1-plane halos; boundary layers on a side stream "
+                                       "concurrent with the interior; transport=" + runner.transport +
+                                       (" (step kernel stores the planes into the neighbours' halos over "
+                                        "NVLink peer pointers, stream-ordered flags)" if runner.transport == "p2p"
+                                        else " (NCCL send/recv)")),
                        "halo_bytes_per_direction": size * size * 32,
                        "l2": "slab state >> 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic("cfg3-slab-1024x64"),
+                         "algorithmic_bytes_per_launch": local_nodes * BYTES_PER_UPDATE,
+                         "peak_source": peak_src,
                          "kernel": "lat_step_kernel (one slab, no communication)",
                          "bytes_per_update": BYTES_PER_UPDATE, "kernel_ms_per_launch": kms},
             "cpu_baseline": None,
@@ -333,6 +407,9 @@ def bench_slabs(args) -> int:
             "checksum_sum_u": float(cs.item()), "checksum_expected": float(args.warmup + args.steps + 1),
         }
         print(json.dumps(line), flush=True)
+    dist.barrier()
+    if runner.transport == "p2p":
+        backend.detach_peers()
     backend.plan.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -302,6 +302,10 @@ def main():
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if os.environ.get("TK_WATCHDOG"):  # diagnostics: dump every thread's stack and exit if the run stalls
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ["TK_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         return reference_arm(args, rank)

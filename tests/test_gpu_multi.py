@@ -24,6 +24,9 @@ def _worker(rank, world, port, out, transport):
     from tetrakis_sim_b200.slab import CudaSlabBackend, SlabRunner, global_max_degree
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if transport == "p2p-split":
+        os.environ["TK_SLAB_SPLIT"] = "1"
+        transport = "p2p"
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     try:
@@ -54,7 +57,7 @@ def _worker(rank, world, port, out, transport):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "p2p-split"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_multi_gpu_slab_run_matches_the_oracle(world, transport, tmp_path):
     import torch

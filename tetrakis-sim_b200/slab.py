@@ -109,6 +109,8 @@ class SlabRunner:
         # neighbours' halos through peer-mapped pointers, synchronised by stream-ordered flags
         self.transport = transport if (dist is not None and world > 1 and comm_stream is not None) else "nccl"
         self._push_count = 0
+        self.interior_first = os.environ.get("TK_SLAB_ORDER", "boundary_first") == "interior_first"
+        self.split = os.environ.get("TK_SLAB_SPLIT", "0") == "1"
         if self.transport == "p2p":
             backend.attach_peers(dist, rank, world, spec)
 
@@ -158,13 +160,15 @@ class SlabRunner:
         if self.transport == "p2p":
             import torch
 
-            ev = torch.cuda.Event()
-            ev.record(self.main_stream)
             self.dist.barrier()  # nobody still reads the halos of a previous run
-            self.comm_stream.wait_event(ev)
-            self.backend.push_halos(self.comm_stream.cuda_stream)
+            st = self.comm_stream if self.split else self.main_stream
+            if self.split:
+                ev = torch.cuda.Event()
+                ev.record(self.main_stream)
+                st.wait_event(ev)
+            self.backend.push_halos(st.cuda_stream)
             self._push_count += 1
-            self.backend.signal(self._push_count, self.comm_stream.cuda_stream)
+            self.backend.signal(self._push_count, st.cuda_stream)
             self._ev_end = torch.cuda.Event()
             self._ev_end.record(self.main_stream)
             return
@@ -221,11 +225,29 @@ class SlabRunner:
         self._ev_end.record(main)
 
     def _step_p2p(self):
-        """Fused boundary update + halo push: no NCCL in the loop.  Flag value k = "k pushes done"."""
+        """Fused boundary update + halo push: no NCCL in the loop.  Flag value k = "k pushes done".
+
+        Default: ONE launch over all owned layers -- the CTAs that update the first / last layer store
+        their results into the neighbours' halos as they go -- then the flag, then the finalise.  All
+        ranks run the same kernel on the same amount of data, so the wait for the neighbours' flag at
+        the top of the next step is a few microseconds; nothing is split, nothing needs overlapping.
+        TK_SLAB_SPLIT=1 keeps the boundary-first / interior-concurrent schedule (needed for NCCL)."""
+        if not self.split:
+            b = self.backend
+            st = self.main_stream.cuda_stream
+            b.wait(self._push_count, st)
+            b.step_layers(0, self.n_local_layers)
+            self._push_count += 1
+            b.signal(self._push_count, st)
+            b.step_end()
+            return
         import torch
 
         L, b = self.n_local_layers, self.backend
         side, main = self.comm_stream, self.main_stream
+        interior_first = self.interior_first
+        if interior_first and L > 2:
+            b.step_layers(1, L - 1)
         side.wait_event(self._ev_end)
         b.wait(self._push_count, side.cuda_stream)  # the neighbours' planes of u_t sit in my halos
         b.step_layers_on(0, 1, side.cuda_stream)  # ... and these launches push u_{t+1} into theirs
@@ -235,7 +257,7 @@ class SlabRunner:
         ev_bnd.record(side)
         self._push_count += 1
         b.signal(self._push_count, side.cuda_stream)
-        if L > 2:
+        if not interior_first and L > 2:
             b.step_layers(1, L - 1)
         main.wait_event(ev_bnd)
         b.step_end()
@@ -293,7 +315,7 @@ def bench_slabs(args) -> int:
     spec = LatticeSpec(size=size, dim=3, layers=per_gpu * world, defect="blackhole", radius=64.0)
 
     main = torch.cuda.current_stream(dev)
-    comm = torch.cuda.Stream(dev, priority=-1)  # boundary layers + NCCL: scheduled ahead of the interior
+    comm = torch.cuda.Stream(dev, priority=int(os.environ.get("TK_SLAB_PRIO", "-1")))  # boundary layers (+ NCCL)
     backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=local)
     mode = os.environ.get("TK_SLAB_MODE", "full")  # diagnostics: "nocomm" skips the exchange, "serial"
     transport = os.environ.get("TK_SLAB_TRANSPORT", "p2p")

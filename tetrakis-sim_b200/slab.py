@@ -314,8 +314,15 @@ def bench_slabs(args) -> int:
     per_gpu = args.layers or 64
     spec = LatticeSpec(size=size, dim=3, layers=per_gpu * world, defect="blackhole", radius=64.0)
 
-    main = torch.cuda.current_stream(dev)
-    comm = torch.cuda.Stream(dev, priority=int(os.environ.get("TK_SLAB_PRIO", "-1")))  # boundary layers (+ NCCL)
+    # a dedicated non-blocking stream: the legacy default stream synchronises implicitly with every
+    # blocking stream of the process, which we do not want around stream-ordered flag waits
+    main = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(main)
+    comm = torch.cuda.Stream(dev, priority=int(os.environ.get("TK_SLAB_PRIO", "-1")))  # split mode: boundary layers (+ NCCL)
+    if not os.environ.get("TK_WATCHDOG"):  # a stalled exchange must fail loudly, not hang the box
+        import faulthandler
+
+        faulthandler.dump_traceback_later(600, exit=True)
     backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=local)
     mode = os.environ.get("TK_SLAB_MODE", "full")  # diagnostics: "nocomm" skips the exchange, "serial"
     transport = os.environ.get("TK_SLAB_TRANSPORT", "p2p")

@@ -304,3 +304,19 @@ def test_energy_is_conserved_without_damping_and_decays_with_it():
         h1 = tk.run_wave_sim(spec, steps=200, initial_data={k: 1.0}, dt=0.01, damping=0.01, energy=True)
     assert np.max(np.abs(h0.energy - h0.energy[0])) < 1e-10 * abs(h0.energy[0])
     assert h0.energy[0] > 0 and h1.energy[-1] < 0.5 * h1.energy[0] and np.mean(np.diff(h1.energy) < 0) > 0.9
+
+
+def test_run_fft_many_equals_per_node_run_fft():
+    """N2: whole-layer spectra in one batched call (notebooks/tetrakis_blackhole_waves.ipynb cells 12-13)."""
+    g = load_golden("t3d_s7l5_blackhole_r2p5")
+    G, labels = graph_from_golden(g)
+    h = tk.run_wave_sim(G, steps=g["steps"], initial_data=_initial_data(g, labels), c=g["c"], dt=g["dt"],
+                        damping=g["damping"])
+    layer = [n for n in labels if n[2] == 2] + [(99, 99, 2, "A")]  # one node that is not in the graph
+    freq, spectra, values, bins = tk.run_fft_many(h, layer)
+    assert spectra.shape == (len(layer), g["steps"] + 1) and not values[-1].any()
+    for i in (0, 7, len(layer) - 2):
+        f1, s1, v1 = tk.run_fft(h, layer[i])
+        assert np.array_equal(f1, freq) and np.array_equal(v1, values[i]) and np.array_equal(s1, spectra[i])
+        assert bins[i] == int(np.argmax(s1))
+    assert rel_inf(spectra, np.abs(np.fft.fft(values, axis=1))) < 1e-12

@@ -7,10 +7,10 @@ from .compiler import compile_graph, compile_lattice, structured_from_graph
 from .ensemble import EnsembleResult, run_ensemble, sweep_grid
 from .install import install, uninstall
 from .lattice import LatticeSpec
-from .physics import SimulationHistory, dominant_frequency, run_fft, run_wave_sim
+from .physics import SimulationHistory, dominant_frequency, run_fft, run_fft_many, run_wave_sim
 
 __all__ = [
-    "run_wave_sim", "run_fft", "SimulationHistory", "dominant_frequency", "LatticeSpec",
+    "run_wave_sim", "run_fft", "run_fft_many", "SimulationHistory", "dominant_frequency", "LatticeSpec",
     "Plan", "compile_graph", "compile_lattice", "structured_from_graph", "dft_abs",
     "device_count", "device_info", "install", "uninstall", "build_library",
     "run_ensemble", "sweep_grid", "EnsembleResult",

@@ -224,7 +224,9 @@ def gpu_single(args):
         raise SystemExit(f"unknown workload {workload}")
     desc = desc.format(spec.size)
     kick = spec.kick_node() if spec.defect != "none" else spec.bench_kick_node()
-    plan = tk.compile_lattice(spec, device=0)
+    f32 = args.dtype == "f32"
+    bpu = BYTES_PER_UPDATE / 2 if f32 else BYTES_PER_UPDATE
+    plan = tk.compile_lattice(spec, device=0, dtype="float32" if f32 else "float64")
     maxdeg = plan.max_degree
     limit = 1.0 / np.sqrt(maxdeg)
     dt_eff = min(dt_req, limit)
@@ -245,7 +247,7 @@ def gpu_single(args):
     kms = out["step_kernel_ms"]
     value = n_updates * args.steps / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
-    achieved = n_updates * BYTES_PER_UPDATE * args.steps / (kms * 1e-3) / 1e9
+    achieved = n_updates * bpu * args.steps / (kms * 1e-3) / 1e9
     checksum = float(plan.get_state().sum()) if spec.num_slots <= 600_000_000 else None
 
     # e2e: the whole run through the C ABI with host buffers (kicks H2D; probe series and the final
@@ -270,15 +272,15 @@ def gpu_single(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "lattice": desc, "nodes": n_updates, "max_degree": maxdeg,
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": workload, "lattice": desc.replace("fp64", "fp32 state (fp64 sums)") if f32 else desc, "nodes": n_updates, "max_degree": maxdeg,
                    "effective_dt": dt_eff, "kick": list(map(str, kick)),
                    "l2": f"state {2 * spec.num_slots * 8 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
                    "tiling": tiling},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(workload), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": n_updates * BYTES_PER_UPDATE,
-                     "kernel": "lat_step_kernel", "bytes_per_update": BYTES_PER_UPDATE,
+                     "frac": achieved / peak, "traffic": None if f32 else ncu_traffic(workload), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": n_updates * bpu,
+                     "kernel": "lat_step_f32_kernel" if f32 else "lat_step_kernel", "bytes_per_update": bpu,
                      "kernel_ms_per_launch": kms / args.steps,
                      "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0},
         "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -288,6 +290,80 @@ def gpu_single(args):
         "checksum_expected": float(args.warmup + args.steps + 1) if spec.defect != "singularity" else None,
     }
     print(json.dumps(line))
+    return 0
+
+
+def gpu_ensemble(args):
+    """--workload cfg5-ensemble: BASELINE configs[4], 65 536 independent 13x13x7 simulations over a
+    radius x damping x dt grid, 50 steps each; simulations are block-distributed over the ranks, no
+    communication on the data path.  One "step" = one complete sweep."""
+    import torch
+
+    import tetrakis_sim_b200 as tk
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    specs, damp, dt = tk.sweep_grid(13, 7, np.linspace(0.5, 4.0, 64), np.linspace(0.0, 0.05, 32),
+                                    np.linspace(0.02, 0.2, 32))
+    sim_steps = 50
+    kms, walls, res = [], [], None
+    clk = ClockSampler(local).start()
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup:
+            clk.mark_begin()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, (lo, hi) = tk.run_ensemble_sharded(specs, sim_steps, c=1.0, dt=dt, damping=damp, dist=dist,
+                                                device=local, gather=False)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if it >= args.warmup:
+            kms.append(res.elapsed_ms)
+            walls.append(wall)
+    clk.__exit__()
+    tot = torch.tensor([float(res.node_updates), max(kms), max(walls), float(np.mean(kms)), float(np.mean(walls))],
+                       dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        upd = tot[:1].clone()
+        dist.all_reduce(upd)
+        mx = tot[1:].clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        tot = torch.cat([upd, mx])
+    updates, _, _, k_mean, w_mean = tot.tolist()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": updates / (k_mean * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": k_mean, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg5-ensemble",
+                       "lattice": "65 536 simulations of 3-D tetrakis 13x13x7 (4 732 nodes), black hole radius in "
+                                  "64 values [0.5, 4] x damping in 32 values [0, 0.05] x dt in 32 values [0.02, 0.2], "
+                                  "50 steps each, probe series + |DFT| + dominant bin per simulation",
+                       "node_updates_per_sweep": updates, "parallelism": f"simulations block-distributed over {world} GPU(s)",
+                       "l2": "state resident in shared memory (no HBM state traffic): the HBM roofline does not apply"},
+            "roofline": {"bound": "hbm", "achieved": updates * BYTES_PER_UPDATE / (k_mean * 1e-3) / 1e9,
+                         "peak": measured_peak_gbs()[0], "unit": "GB/s",
+                         "frac": updates * BYTES_PER_UPDATE / (k_mean * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                         "traffic": None, "kernel": "ensemble_kernel",
+                         "note": "nominal 24 B/update for comparability only; the state never leaves the SM"},
+            "cpu_baseline": None,
+            "e2e": {"value": updates / w_mean / 1e9, "unit": UNIT, "seconds": w_mean,
+                    "h2d_bytes_per_step": 65536 * 24.0 + 64 * 1183, "d2h_bytes_per_step": 65536 * (2 * 51 + 1) * 8.0,
+                    "includes": "mask/parameter upload, kernel, series + spectra + dominant bins D2H"},
+            "gpu_launches": args.steps, "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -301,6 +377,8 @@ def main():
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f32 = optional fp32 state mode (12 B/update; NOT the parity mode)")
     args = ap.parse_args()
     if os.environ.get("TK_WATCHDOG"):  # diagnostics: dump every thread's stack and exit if the run stalls
         import faulthandler
@@ -309,6 +387,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         return reference_arm(args, rank)
+    if args.workload == "cfg5-ensemble":
+        return gpu_ensemble(args)
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return gpu_single(args)
     from tetrakis_sim_b200.slab import bench_slabs  # multi-GPU: layer slabs + halo exchange

@@ -89,6 +89,12 @@ typedef struct tk_lattice_desc {
 
 int tk_lattice_plan_create(int device, const tk_lattice_desc *desc, tk_plan **out);
 
+/* Same with option flags.  TK_PLAN_F32: optional fp32 mode -- the state is stored and updated in
+ * fp32 (12 B per node-update instead of 24), row/column sums and the Laplacian stay fp64.  The ABI
+ * keeps double for every host-side array; tolerance vs fp64: DESIGN.md section 4. */
+#define TK_PLAN_F32 0x1u
+int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *desc, uint32_t flags, tk_plan **out);
+
 /* ------------------------------------------------------------------------------------------
  * Common plan API
  * ------------------------------------------------------------------------------------------ */

@@ -4,7 +4,7 @@ from ._build import build_library
 from ._lib import (BackendUnavailable, NoDeviceError, Plan, TkError, device_count, device_info,
                    dft_abs)
 from .compiler import compile_graph, compile_lattice, structured_from_graph
-from .ensemble import EnsembleResult, run_ensemble, sweep_grid
+from .ensemble import EnsembleResult, run_ensemble, run_ensemble_sharded, sweep_grid
 from .install import install, uninstall
 from .lattice import LatticeSpec
 from .physics import SimulationHistory, dominant_frequency, run_fft, run_fft_many, run_wave_sim
@@ -13,6 +13,6 @@ __all__ = [
     "run_wave_sim", "run_fft", "run_fft_many", "SimulationHistory", "dominant_frequency", "LatticeSpec",
     "Plan", "compile_graph", "compile_lattice", "structured_from_graph", "dft_abs",
     "device_count", "device_info", "install", "uninstall", "build_library",
-    "run_ensemble", "sweep_grid", "EnsembleResult",
+    "run_ensemble", "run_ensemble_sharded", "sweep_grid", "EnsembleResult",
     "BackendUnavailable", "NoDeviceError", "TkError",
 ]  # fmt: skip

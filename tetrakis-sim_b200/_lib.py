@@ -20,7 +20,7 @@ TK_OK, TK_ERR_INVALID, TK_ERR_CUDA, TK_ERR_NOMEM, TK_ERR_NO_DEVICE = 0, 1, 2, 3,
 # every symbol declared in include/tetrakis_b200.h (tests check the .so exports all of them)
 ABI_SYMBOLS = (
     "tk_abi_version", "tk_last_error", "tk_device_count", "tk_device_info",
-    "tk_graph_plan_create", "tk_lattice_plan_create",
+    "tk_graph_plan_create", "tk_lattice_plan_create", "tk_lattice_plan_create_ex",
     "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
     "tk_plan_run", "tk_plan_launch_count", "tk_plan_destroy",
@@ -96,6 +96,7 @@ def lib():
                                  POINTER(c_int), POINTER(c_int64)]  # fmt: skip
     L.tk_graph_plan_create.argtypes = [c_int, c_int64, P, P, P, P, P, POINTER(P)]
     L.tk_lattice_plan_create.argtypes = [c_int, POINTER(LatticeDesc), POINTER(P)]
+    L.tk_lattice_plan_create_ex.argtypes = [c_int, POINTER(LatticeDesc), ctypes.c_uint32, POINTER(P)]
     L.tk_plan_set_stream.argtypes = [P, P]
     L.tk_plan_num_nodes.argtypes = [P, POINTER(c_int64)]
     L.tk_plan_max_degree.argtypes = [P, POINTER(c_int64)]
@@ -175,6 +176,7 @@ class Plan:
     def __init__(self, handle, kind: str):
         self._h = handle
         self.kind = kind
+        self.f32 = False  # optional fp32 state (lattice plans only)
 
     # -- construction -------------------------------------------------------------------------
     @classmethod
@@ -195,7 +197,7 @@ class Plan:
     @classmethod
     def lattice(cls, size, layers, *, z_begin=0, z_end=None, special_index=None,
                 special_flags=None, special_inv_mass=None, special_potential=None, corr=None,
-                device: int = 0) -> "Plan":  # fmt: skip
+                device: int = 0, f32: bool = False) -> "Plan":  # fmt: skip
         si = _arr(special_index if special_index is not None else [], np.int64)
         sf = _arr(special_flags if special_flags is not None else [], np.uint8)
         sm = _arr(special_inv_mass, np.float64)
@@ -210,8 +212,10 @@ class Plan:
                         int(layers if z_end is None else z_end), len(si), _p(si), _p(sf), _p(sm),
                         _p(sv), len(ca), _p(ca), _p(cb), _p(cs))  # fmt: skip
         h = c_void_p()
-        check(lib().tk_lattice_plan_create(device, ctypes.byref(d), ctypes.byref(h)))
-        return cls(h, "lattice")
+        check(lib().tk_lattice_plan_create_ex(device, ctypes.byref(d), 1 if f32 else 0, ctypes.byref(h)))
+        plan = cls(h, "lattice")
+        plan.f32 = bool(f32)
+        return plan
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):

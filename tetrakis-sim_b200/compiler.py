@@ -68,12 +68,16 @@ def compile_graph(G, device: int = 0) -> CompiledGraph:
     return CompiledGraph(plan, nodes, index, max_degree)
 
 
-def compile_lattice(spec: LatticeSpec, device: int = 0, z_begin: int = 0, z_end: int | None = None) -> Plan:
+def compile_lattice(spec: LatticeSpec, device: int = 0, z_begin: int = 0, z_end: int | None = None,
+                    dtype: str = "float64") -> Plan:
+    """``dtype="float32"`` selects the optional fp32 state mode (12 B per update, fp64 sums/Laplacian)."""
+    if dtype not in ("float64", "float32"):
+        raise ValueError("dtype must be 'float64' or 'float32'")
     idx, flags, im, pot = spec.specials()
     return Plan.lattice(
         spec.size, spec.layers, z_begin=z_begin, z_end=z_end, special_index=idx,
         special_flags=flags, special_inv_mass=im, special_potential=pot,
-        corr=spec.corrections(), device=device,
+        corr=spec.corrections(), device=device, f32=dtype == "float32",
     )  # fmt: skip
 
 

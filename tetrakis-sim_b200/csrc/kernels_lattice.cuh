@@ -109,6 +109,49 @@ __device__ __noinline__ void cell_update_detail(const LatDev &P, const double *_
     }
 }
 
+// Same for the fp32 state layout: identical arithmetic in fp64, the correction partners are read as floats.
+__device__ __noinline__ void cell_update_detail_f32(const LatDev &P, const float *__restrict__ ustate,
+                                                    int det, int cell_in_tab, long long node0,
+                                                    unsigned f, double coeff, double damping, CellIO &io)
+{
+    double cell = 0.0;
+    io.e = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if ((f >> q) & 1u) cell += io.uq[q];
+    const double ccnt = (double)__popc(f & 0xFu);
+    int attr = -1;
+    int2 cr = make_int2(0, 0);
+    if (det >= 0) {
+        attr = P.det_attr[det];
+        cr = P.det_corr[det];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const bool part = (f >> q) & 1u, alive = (f >> (4 + q)) & 1u;
+        const double uq = io.uq[q], upq = io.upq[q];
+        double lap = 0.0;
+        if (part) {
+            const bool pm = (f >> (8 + q)) & 1u, pp = (f >> (12 + q)) & 1u;
+            double nsum = (cell - uq) + (io.RS[q] - uq) + (io.CS[q] - uq);
+            double deg = (ccnt - 1.0) + (io.RC[q] - 1.0) + (io.CC[q] - 1.0);
+            if (pm) { nsum += io.zm[q]; deg += 1.0; }
+            if (pp) { nsum += io.zp[q]; deg += 1.0; }
+            lap = nsum - deg * uq;
+        }
+        for (int k = cr.x; k < cr.y; ++k)
+            if (P.corr_a[k] == node0 + q) lap += P.corr_sign[k] * ((double)ustate[P.corr_b[k]] - uq);
+        double im = 1.0, v = 0.0;
+        if (attr >= 0) {
+            im = P.attr_im[(size_t)attr * 256 + cell_in_tab * 4 + q];
+            v = P.attr_v[(size_t)attr * 256 + cell_in_tab * 4 + q];
+        }
+        const double r = 2.0 * uq - upq + (coeff * im) * lap - (coeff * v) * uq - damping * (uq - upq);
+        io.un[q] = alive ? r : 0.0;
+        io.pun[q] = part ? io.un[q] : 0.0;
+    }
+}
+
 // MODE 0: leapfrog step.  MODE 1: sums only (row/col sums of the current state, no update).
 template <int CPL, int WC, bool K3D, int MODE, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB)
@@ -287,6 +330,134 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
     }
 }
 
+// fp32 state variant of lat_step_kernel (optional mode; 12 B/update).
+//
+// Storage and the update expression are fp32; the Laplacian -- a difference of two sums of up to
+// ~16 000 terms -- is formed in fp64 from the fp64 row/column sums (which are accumulated and kept in
+// fp64 exactly as in the fp64 path) and rounded once, so the only fp32 errors are the per-step
+// rounding of the state itself.  One cell per lane (16-byte LDG/STG.128), same tiling, same partial
+// sum layout, same defect tables, same peer halo push as the fp64 kernel.  Tolerance: see
+// tests/test_gpu_fp32.py (documented in DESIGN.md).
+template <int WC, bool K3D, int MODE, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+lat_step_f32_kernel(const __grid_constant__ LatDev P, const float *__restrict__ u,
+                    float *__restrict__ w, double *__restrict__ prow, double *__restrict__ pcol,
+                    double coeff, double damping, int zl_begin, int zl_end, int rchunk, int nchunk,
+                    int nsegk, int nct, int nzg, int pf_rows)
+{
+    constexpr int WZ = 8 / WC;
+    constexpr bool STEP = MODE != 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b = blockIdx.x;
+    const int zg = b % nzg;
+    b /= nzg;
+    const int ct = b % nct;
+    const int ch = b / nct;
+    const int zl = zl_begin + zg * WZ + warp / WC;
+    const int segk = ct * WC + warp % WC;
+    if (zl >= zl_end || segk >= nsegk) return;
+
+    const int S = P.S;
+    const int c0 = segk * 32 + lane;
+    const bool valid = c0 < S;
+    const size_t plane = (size_t)S * S * 4;
+    const size_t zbase = (size_t)(zl + P.halo) * plane;
+    const unsigned fplain = plain_flags(P, zl);
+    const bool zm_on = K3D && (fplain & 0x100u), zp_on = K3D && (fplain & 0x1000u);
+    const double degbase = 4.0 + (zm_on ? 1.0 : 0.0) + (zp_on ? 1.0 : 0.0);
+    const float coeff_f = (float)coeff, damp_f = (float)damping;
+    float *peer_lo = reinterpret_cast<float *>(P.peer_lo), *peer_hi = reinterpret_cast<float *>(P.peer_hi);
+
+    double CS[4] = {0, 0, 0, 0}, CC[4] = {0, 0, 0, 0}, cacc[4] = {0, 0, 0, 0};
+    if (STEP && valid) {
+        ld256_nc(P.colinfo + ((size_t)zl * S + c0) * 8, CS);
+        ld256_nc(P.colinfo + ((size_t)zl * S + c0) * 8 + 4, CC);
+    }
+    const int r_begin = ch * rchunk;
+    const int r_end = min(S, r_begin + rchunk);
+    const int tab0 = c0 / kTabSeg;
+    const bool pf_lane = STEP && pf_rows > 0 && valid && (lane & 7) == 0;  // one request per 128 B
+    if (pf_lane) {
+        for (int r = r_begin; r < min(r_end, r_begin + pf_rows); ++r) {
+            const size_t o = zbase + ((size_t)r * S + c0) * 4;
+            prefetch_l2(u + o);
+            prefetch_l2(w + o);
+        }
+    }
+    for (int r = r_begin; r < r_end; ++r) {
+        const size_t rowoff = zbase + ((size_t)r * S + c0) * 4;
+        if (pf_lane && r + pf_rows < r_end) {
+            const size_t o = rowoff + (size_t)pf_rows * S * 4;
+            prefetch_l2(u + o);
+            prefetch_l2(w + o);
+        }
+        float4 uq = make_float4(0.f, 0.f, 0.f, 0.f), upq = uq, zm = uq, zp = uq;
+        if (valid) {
+            uq = ld128_nc(u + rowoff);
+            if (STEP) {
+                upq = ld128_cs(w + rowoff);
+                if (zm_on) zm = ld128_nc(u + rowoff - plane);
+                if (zp_on) zp = ld128_nc(u + rowoff + plane);
+            }
+        }
+        int det = -1;
+        if (valid) det = P.seg_flag[((size_t)zl * S + r) * P.ntab + tab0];
+        const bool all_plain = __all_sync(0xffffffffu, det < 0);
+        double RS[4] = {0, 0, 0, 0}, RC[4] = {0, 0, 0, 0};
+        if (STEP) {
+            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8, RS);
+            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8 + 4, RC);
+        }
+        const float uf[4] = {uq.x, uq.y, uq.z, uq.w}, upf[4] = {upq.x, upq.y, upq.z, upq.w};
+        const float zmf[4] = {zm.x, zm.y, zm.z, zm.w}, zpf[4] = {zp.x, zp.y, zp.z, zp.w};
+        float un[4];
+        double pun[4];
+        if (MODE == 1) {
+            unsigned f = fplain;
+            if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + (c0 & (kTabSeg - 1))];
+            if (!valid) f = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pun[q] = ((f >> q) & 1u) ? (double)uf[q] : 0.0;
+        } else if (all_plain) {
+            const double cell = (double)((uf[0] + uf[1]) + (uf[2] + uf[3]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double zz = K3D ? (double)(zmf[q] + zpf[q]) : 0.0;
+                const double nb = (cell + RS[q]) + (CS[q] + zz);
+                const double dg = (RC[q] + degbase) + CC[q];
+                const float lap = (float)(nb - dg * (double)uf[q]);
+                un[q] = 2.0f * uf[q] - upf[q] + coeff_f * lap - damp_f * (uf[q] - upf[q]);
+                pun[q] = valid ? (double)un[q] : 0.0;
+            }
+        } else {
+            unsigned f = fplain;
+            if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + (c0 & (kTabSeg - 1))];
+            if (!valid) f = 0;
+            CellIO io;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                io.uq[q] = uf[q]; io.upq[q] = upf[q]; io.zm[q] = zmf[q]; io.zp[q] = zpf[q];
+                io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[q]; io.CC[q] = CC[q];
+            }
+            cell_update_detail_f32(P, u, det, c0 & (kTabSeg - 1), (long long)rowoff, f, coeff, damping, io);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { un[q] = (float)io.un[q]; pun[q] = ((f >> q) & 1u) ? (double)un[q] : 0.0; }
+        }
+        if (STEP && valid) {
+            const float4 v = make_float4(un[0], un[1], un[2], un[3]);
+            st128_cs(w + rowoff, v);
+            if (K3D) {
+                if (zl == 0 && peer_lo) st128(peer_lo + (rowoff - zbase), v);
+                if (zl == P.Lloc - 1 && peer_hi) st128(peer_hi + (rowoff - zbase), v);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cacc[q] += pun[q];
+        warp_sum4_store(pun, lane, prow + (((size_t)zl * S + r) * nsegk + segk) * 4);
+    }
+    if (valid) st256(pcol + (((size_t)zl * nchunk + ch) * S + c0) * 4, cacc);
+}
+
 // 3-D step with explicit on-chip sharing of the z neighbours (cp.async multi-stage pipeline).
 //
 // In 3-D every node also reads u(z-1) and u(z+1): 40 B/update through L2 if left to the caches
@@ -461,12 +632,14 @@ __global__ void __launch_bounds__(256)
 lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, int nrowblk,
                     const double *__restrict__ prow, const double *__restrict__ pcol,
                     double *__restrict__ rowinfo, double *__restrict__ colinfo,
-                    const double *__restrict__ state, const long long *__restrict__ probe_idx,
-                    int n_probes, double *__restrict__ probe_row, const double *__restrict__ pen,
-                    long long n_pen, double *__restrict__ energy_out)
+                    const void *__restrict__ state, int state_is_f32,
+                    const long long *__restrict__ probe_idx, int n_probes, double *__restrict__ probe_row,
+                    const double *__restrict__ pen, long long n_pen, double *__restrict__ energy_out)
 {
     if (blockIdx.x == 0)
-        for (int t = threadIdx.x; t < n_probes; t += blockDim.x) probe_row[t] = state[probe_idx[t]];
+        for (int t = threadIdx.x; t < n_probes; t += blockDim.x)
+            probe_row[t] = state_is_f32 ? (double)static_cast<const float *>(state)[probe_idx[t]]
+                                        : static_cast<const double *>(state)[probe_idx[t]];
     if (blockIdx.x == gridDim.x - 1 && energy_out != nullptr) {
         // last CTA: staggered energy E_{t+1/2} = 1/2 * sum of the per-warp partials, fixed order
         __shared__ double red[256];
@@ -577,6 +750,26 @@ __global__ void scatter_kernel(double *__restrict__ dst, const long long *__rest
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[idx[i]] = val[i];
+}
+
+__global__ void scatter_f32_kernel(float *__restrict__ dst, const long long *__restrict__ idx,
+                                   const double *__restrict__ val, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx[i]] = (float)val[i];
+}
+
+// fp32 state <-> fp64 staging (set_state / get_state / history of an fp32 plan)
+__global__ void f32_to_f64_kernel(const float *__restrict__ src, double *__restrict__ dst, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (double)src[i];
+}
+
+__global__ void f64_to_f32_kernel(const double *__restrict__ src, float *__restrict__ dst, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
 }
 
 __global__ void gather_kernel(const double *__restrict__ src, const long long *__restrict__ idx,

@@ -92,7 +92,8 @@ struct tk_plan {
     long long n = 0;          // local nodes visible through the ABI
     long long alloc = 0;      // doubles per state buffer
     long long state_off = 0;  // ABI index 0 lives at this offset in a state buffer
-    double *buf[2] = {nullptr, nullptr};
+    double *buf[2] = {nullptr, nullptr};  // raw state storage; fp32 plans reinterpret it as float
+    int esz = 8;                          // bytes per state element: 8 (fp64) or 4 (optional fp32 mode)
     int cur = 0;  // buf[cur] = u_t, buf[cur^1] = u_{t-1} (overwritten by u_{t+1})
     long long launches = 0;
     long long max_degree = -1;
@@ -134,6 +135,14 @@ struct tk_plan {
 };
 
 namespace {
+
+inline bool is_f32(const tk_plan *p) { return p->esz == 4; }
+// address of element `off` of state buffer b (buffers are typed by p->esz)
+inline char *bptr(const tk_plan *p, int b, long long off) { return reinterpret_cast<char *>(p->buf[b]) + (size_t)off * p->esz; }
+inline char *pptr(const tk_plan *p, int side, int b, long long off)
+{
+    return reinterpret_cast<char *>(p->peer_buf[side][b]) + (size_t)off * p->esz;
+}
 
 int plan_common_init(tk_plan *p, int device)
 {
@@ -189,15 +198,26 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
     }
     cudaStream_t st = p->launch_stream ? p->launch_stream : p->stream;
     if (K3D && MODE != 1) {
-        const size_t plane = (size_t)p->lat.S * p->lat.S * 4;
+        const long long plane = (long long)p->lat.S * p->lat.S * 4;
         const int nb = p->cur ^ 1;  // every rank swaps in lockstep, so buffer parities agree
-        p->lat.peer_lo = p->peer_buf[0][nb] ? p->peer_buf[0][nb] + (size_t)(p->peer_layers[0] + 1) * plane : nullptr;
+        p->lat.peer_lo = p->peer_buf[0][nb] ? reinterpret_cast<double *>(pptr(p, 0, nb, (p->peer_layers[0] + 1) * plane)) : nullptr;
         p->lat.peer_hi = p->peer_buf[1][nb] ? p->peer_buf[1][nb] : nullptr;
     }
-    tk::lat_step_kernel<CPL, WC, K3D, MODE, MINB><<<(unsigned)grid, 256, 0, st>>>(
-        p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
-        zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg, p->pf_rows, pen,
-        p->coeff > 0.0 ? 1.0 / p->coeff : 0.0);
+    if (is_f32(p)) {
+        if (CPL != 1 || MODE == 2)
+            return fail(TK_ERR_INVALID, "fp32 plans support cells_per_lane = 1 and no energy series");
+        constexpr int FM = (CPL == 1 && MODE != 2) ? MODE : 0;
+        constexpr int FB = (MINB >= 2 && MINB <= 4) ? MINB : 3;
+        tk::lat_step_f32_kernel<WC, K3D, FM, FB><<<(unsigned)grid, 256, 0, st>>>(
+            p->lat, reinterpret_cast<const float *>(p->buf[p->cur]), reinterpret_cast<float *>(p->buf[p->cur ^ 1]),
+            p->prow, p->pcol, p->coeff, p->damping, zl_begin, zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg,
+            p->pf_rows);
+    } else {
+        tk::lat_step_kernel<CPL, WC, K3D, MODE, MINB><<<(unsigned)grid, 256, 0, st>>>(
+            p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,
+            zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg, p->pf_rows, pen,
+            p->coeff > 0.0 ? 1.0 / p->coeff : 0.0);
+    }
     p->launches++;
     TK_CUDA(cudaGetLastError());
     return TK_OK;
@@ -347,7 +367,8 @@ int lat_finalise(tk_plan *p, const double *state, double *probe_row)
         eout = p->energy_series + p->energy_row++;
     tk::lat_finalise_kernel<<<(unsigned)(nrowblk + ncolblk + (eout ? 1 : 0)), 256, 0, p->stream>>>(
         p->lat.S, p->lat.Lloc, p->nsegk, p->nchunk, nrowblk, p->prow, p->pcol, p->rowinfo, p->colinfo,
-        state, p->probe_idx, probe_row ? p->n_probes : 0, probe_row, p->pen, p->pen_used, eout);
+        state, is_f32(p) ? 1 : 0, p->probe_idx, probe_row ? p->n_probes : 0, probe_row, p->pen, p->pen_used,
+        eout);
     p->pen_used = 0;
     p->launches++;
     TK_CUDA(cudaGetLastError());
@@ -434,6 +455,46 @@ int graph_step(tk_plan *p, double coeff, double damping)
         p->launches++;
         TK_CUDA(cudaGetLastError());
     }
+    return TK_OK;
+}
+
+// fp32 plans keep the ABI in double: dense state moves through a bounded fp64 staging buffer
+constexpr long long kStageElems = 1LL << 24;
+
+int stage_f64_to_f32(tk_plan *p, const double *host, int b)
+{
+    double *d = nullptr;
+    TK_CUDA(cudaMalloc((void **)&d, (size_t)std::min<long long>(p->n, kStageElems) * sizeof(double)));
+    cudaError_t e = cudaSuccess;
+    for (long long o = 0; o < p->n && e == cudaSuccess; o += kStageElems) {
+        const long long m = std::min<long long>(kStageElems, p->n - o);
+        e = cudaMemcpyAsync(d, host + o, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, p->stream);
+        if (e != cudaSuccess) break;
+        tk::f64_to_f32_kernel<<<1024, 256, 0, p->stream>>>(d, reinterpret_cast<float *>(bptr(p, b, p->state_off + o)), m);
+        p->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    }
+    cudaFree(d);
+    TK_CUDA(e);
+    return TK_OK;
+}
+
+int stage_f32_to_f64(tk_plan *p, int b, double *host)
+{
+    double *d = nullptr;
+    TK_CUDA(cudaMalloc((void **)&d, (size_t)std::min<long long>(p->n, kStageElems) * sizeof(double)));
+    cudaError_t e = cudaSuccess;
+    for (long long o = 0; o < p->n && e == cudaSuccess; o += kStageElems) {
+        const long long m = std::min<long long>(kStageElems, p->n - o);
+        tk::f32_to_f64_kernel<<<1024, 256, 0, p->stream>>>(reinterpret_cast<const float *>(bptr(p, b, p->state_off + o)), d, m);
+        p->launches++;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host + o, d, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    }
+    cudaFree(d);
+    TK_CUDA(e);
     return TK_OK;
 }
 
@@ -537,7 +598,13 @@ int tk_graph_plan_create(int device, int64_t n, const int64_t *rowptr, const int
 // ------------------------------------------------------------------------------ lattice plan
 int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
 {
+    return tk_lattice_plan_create_ex(device, d, 0, out);
+}
+
+int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t flags, tk_plan **out)
+{
     TK_REQUIRE(out, "out is NULL");
+    TK_REQUIRE((flags & ~(uint32_t)TK_PLAN_F32) == 0, "unknown plan flags 0x%x", flags);
     *out = nullptr;
     TK_REQUIRE(d, "desc is NULL");
     TK_REQUIRE(d->size >= 1 && d->layers >= 1, "size and layers must be >= 1");
@@ -555,6 +622,7 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
 
     tk_plan *p = new tk_plan();
     p->kind = kLattice;
+    p->esz = (flags & TK_PLAN_F32) ? 4 : 8;
     p->n = Lloc * plane;
     p->alloc = planes * plane;
     p->state_off = halo * plane;
@@ -711,7 +779,12 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? (halo ? 2 : 3) : 1);
     p->pf_rows = env_int("TK_LAT_PREFETCH", halo ? 2 : 1);
     if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 1; p->wc = halo ? 1 : 8; p->minb = 3; }
-    if (halo && env_int("TK_LAT3D", 0)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
+    if (p->esz == 4) {  // fp32: one cell per lane, 2-3 CTAs/SM; the staged 3-D kernel is fp64-only
+        p->cpl = 1;
+        if (p->minb < 2 || p->minb > 4) p->minb = 3;
+        if (!lat_supported(p->cpl, p->wc, p->minb)) { p->wc = halo ? 1 : 8; p->minb = halo ? 2 : 3; }
+    }
+    if (halo && p->esz == 8 && env_int("TK_LAT3D", 0)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
         p->wz3d = env_int("TK_LAT3D_WZ", 8);
         p->stages3d = env_int("TK_LAT3D_STAGES", 4);
         p->minb3d = env_int("TK_LAT3D_MINB", p->wz3d == 16 ? 1 : (p->wz3d == 4 ? 4 : 2));
@@ -760,9 +833,12 @@ int tk_lattice_plan_create(int device, const tk_lattice_desc *d, tk_plan **out)
     TK_TRY(plan_upload(p, &p->colinfo, colinfo));
     TK_TRY(plan_alloc(p, &p->prow, (size_t)Lloc * S * nsegk_max * 4, true));
     TK_TRY(plan_alloc(p, &p->pcol, (size_t)Lloc * nchunk_alloc * S * 4, true));
-    TK_TRY(plan_alloc(p, &p->buf[0], (size_t)p->alloc + 32, true));  // + 256 B: halo arrival flags
-    p->flags = reinterpret_cast<unsigned long long *>(p->buf[0] + p->alloc);
-    TK_TRY(plan_alloc(p, &p->buf[1], (size_t)p->alloc, true));
+    {   // state buffers are typed by p->esz; buffer 0 carries 256 B of halo arrival flags at its tail
+        const size_t bytes = ((size_t)p->alloc * p->esz + 255) / 256 * 256;
+        TK_TRY(plan_alloc(p, reinterpret_cast<char **>(&p->buf[0]), bytes + 256, true));
+        p->flags = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(p->buf[0]) + bytes);
+        TK_TRY(plan_alloc(p, reinterpret_cast<char **>(&p->buf[1]), bytes, true));
+    }
 
     tk::LatDev &P = p->lat;
     P.S = (int)S; P.Lloc = (int)Lloc; P.halo = (int)halo; P.ntab = ntab;
@@ -822,8 +898,8 @@ int tk_plan_set_state_sparse(tk_plan *p, int64_t n, const int64_t *index, const 
     TK_REQUIRE(p, "plan is NULL");
     TK_REQUIRE(n == 0 || (index && value), "NULL kick arrays");
     TK_CUDA(cudaSetDevice(p->device));
-    TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * sizeof(double), p->stream));
-    TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * sizeof(double), p->stream));
+    TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * p->esz, p->stream));
+    TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * p->esz, p->stream));
     p->cur = 0;
     if (n > 0) {
         std::vector<long long> h(n);
@@ -839,7 +915,11 @@ int tk_plan_set_state_sparse(tk_plan *p, int64_t n, const int64_t *index, const 
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, h.data(), n * sizeof(long long), cudaMemcpyHostToDevice, p->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, value, n * sizeof(double), cudaMemcpyHostToDevice, p->stream);
         if (e == cudaSuccess) {
-            tk::scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(p->buf[0], d_idx, d_val, n);
+            if (is_f32(p))
+                tk::scatter_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(
+                    reinterpret_cast<float *>(p->buf[0]), d_idx, d_val, n);
+            else
+                tk::scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(p->buf[0], d_idx, d_val, n);
             p->launches++;
             e = cudaGetLastError();
         }
@@ -855,14 +935,20 @@ int tk_plan_set_state(tk_plan *p, const double *u, const double *u_prev)
 {
     TK_REQUIRE(p && u, "NULL argument");
     TK_CUDA(cudaSetDevice(p->device));
-    TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * sizeof(double), p->stream));
-    TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * sizeof(double), p->stream));
+    TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * p->esz, p->stream));
+    TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * p->esz, p->stream));
     p->cur = 0;
-    TK_CUDA(cudaMemcpyAsync(p->buf[0] + p->state_off, u, (size_t)p->n * sizeof(double),
-                            cudaMemcpyHostToDevice, p->stream));
-    if (u_prev)
-        TK_CUDA(cudaMemcpyAsync(p->buf[1] + p->state_off, u_prev, (size_t)p->n * sizeof(double),
+    if (is_f32(p)) {
+        int rc = stage_f64_to_f32(p, u, 0);
+        if (rc == TK_OK && u_prev) rc = stage_f64_to_f32(p, u_prev, 1);
+        if (rc) return rc;
+    } else {
+        TK_CUDA(cudaMemcpyAsync(p->buf[0] + p->state_off, u, (size_t)p->n * sizeof(double),
                                 cudaMemcpyHostToDevice, p->stream));
+        if (u_prev)
+            TK_CUDA(cudaMemcpyAsync(p->buf[1] + p->state_off, u_prev, (size_t)p->n * sizeof(double),
+                                    cudaMemcpyHostToDevice, p->stream));
+    }
     if (!p->dead_local.empty()) {  // removed nodes never carry amplitude
         const long long nd = (long long)p->dead_local.size();
         std::vector<long long> h(nd);
@@ -876,8 +962,13 @@ int tk_plan_set_state(tk_plan *p, const double *u, const double *u_prev)
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_val, z.data(), nd * sizeof(double), cudaMemcpyHostToDevice, p->stream);
         if (e == cudaSuccess) {
             const unsigned g = (unsigned)((nd + 255) / 256);
-            tk::scatter_kernel<<<g, 256, 0, p->stream>>>(p->buf[0], d_idx, d_val, nd);
-            tk::scatter_kernel<<<g, 256, 0, p->stream>>>(p->buf[1], d_idx, d_val, nd);
+            if (is_f32(p)) {
+                tk::scatter_f32_kernel<<<g, 256, 0, p->stream>>>(reinterpret_cast<float *>(p->buf[0]), d_idx, d_val, nd);
+                tk::scatter_f32_kernel<<<g, 256, 0, p->stream>>>(reinterpret_cast<float *>(p->buf[1]), d_idx, d_val, nd);
+            } else {
+                tk::scatter_kernel<<<g, 256, 0, p->stream>>>(p->buf[0], d_idx, d_val, nd);
+                tk::scatter_kernel<<<g, 256, 0, p->stream>>>(p->buf[1], d_idx, d_val, nd);
+            }
             p->launches += 2;
             e = cudaGetLastError();
         }
@@ -894,6 +985,12 @@ int tk_plan_get_state(tk_plan *p, double *u, double *u_prev)
 {
     TK_REQUIRE(p, "plan is NULL");
     TK_CUDA(cudaSetDevice(p->device));
+    if (is_f32(p)) {
+        int rc = TK_OK;
+        if (u) rc = stage_f32_to_f64(p, p->cur, u);
+        if (rc == TK_OK && u_prev) rc = stage_f32_to_f64(p, p->cur ^ 1, u_prev);
+        return rc;
+    }
     if (u)
         TK_CUDA(cudaMemcpyAsync(u, p->buf[p->cur] + p->state_off, (size_t)p->n * sizeof(double),
                                 cudaMemcpyDeviceToHost, p->stream));
@@ -909,13 +1006,13 @@ int tk_lattice_halo_ptrs(tk_plan *p, int32_t next_state, void **send_lo, void **
 {
     TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
     TK_REQUIRE(p->lat.halo, "2-D sheets have no halo planes");
-    const size_t plane = (size_t)p->lat.S * p->lat.S * 4;
-    double *b = p->buf[next_state ? (p->cur ^ 1) : p->cur];
-    if (recv_lo) *recv_lo = b;
-    if (send_lo) *send_lo = b + plane;
-    if (send_hi) *send_hi = b + plane * p->lat.Lloc;
-    if (recv_hi) *recv_hi = b + plane * (p->lat.Lloc + 1);
-    if (plane_bytes) *plane_bytes = (int64_t)(plane * sizeof(double));
+    const long long plane = (long long)p->lat.S * p->lat.S * 4;
+    const int b = next_state ? (p->cur ^ 1) : p->cur;
+    if (recv_lo) *recv_lo = bptr(p, b, 0);
+    if (send_lo) *send_lo = bptr(p, b, plane);
+    if (send_hi) *send_hi = bptr(p, b, plane * p->lat.Lloc);
+    if (recv_hi) *recv_hi = bptr(p, b, plane * (p->lat.Lloc + 1));
+    if (plane_bytes) *plane_bytes = (int64_t)(plane * p->esz);
     return TK_OK;
 }
 
@@ -972,6 +1069,7 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     TK_CUDA(cudaSetDevice(p->device));
     int rc = set_probes(p, a->n_probes, a->probe_index, a->steps + 1);
     if (rc) return rc;
+    TK_REQUIRE(!(is_f32(p) && a->energy_out), "the energy series is fp64-only");
     rc = set_energy(p, a->energy_out != nullptr && a->steps > 0, a->steps);
     if (rc) return rc;
 
@@ -986,8 +1084,16 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     long long hist_fill = 0, hist_done = 0;
     auto record = [&]() -> cudaError_t {
         if (!d_hist) return cudaSuccess;
-        cudaError_t e = cudaMemcpyAsync(d_hist + (size_t)hist_fill * p->n, p->buf[p->cur] + p->state_off,
-                                        row_bytes, cudaMemcpyDeviceToDevice, p->stream);
+        cudaError_t e = cudaSuccess;
+        if (is_f32(p)) {
+            tk::f32_to_f64_kernel<<<1024, 256, 0, p->stream>>>(
+                reinterpret_cast<const float *>(bptr(p, p->cur, p->state_off)), d_hist + (size_t)hist_fill * p->n, p->n);
+            p->launches++;
+            e = cudaGetLastError();
+        } else {
+            e = cudaMemcpyAsync(d_hist + (size_t)hist_fill * p->n, p->buf[p->cur] + p->state_off, row_bytes,
+                                cudaMemcpyDeviceToDevice, p->stream);
+        }
         if (e != cudaSuccess) return e;
         if (++hist_fill == chunk_rows) {
             e = cudaMemcpyAsync(a->history_out + (size_t)hist_done * p->n, d_hist,
@@ -1167,13 +1273,14 @@ int tk_lattice_push_halos(tk_plan *p, void *cuda_stream)
     TK_REQUIRE(p && p->kind == kLattice && p->lat.halo, "needs a 3-D lattice plan");
     TK_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : p->stream;
-    const size_t plane = (size_t)p->lat.S * p->lat.S * 4, bytes = plane * sizeof(double);
+    const long long plane = (long long)p->lat.S * p->lat.S * 4;
+    const size_t bytes = (size_t)plane * p->esz;
     const int b = p->cur;
     if (p->peer_buf[0][b])  // my first owned plane -> lower neighbour's upper halo
-        TK_CUDA(cudaMemcpyAsync(p->peer_buf[0][b] + (size_t)(p->peer_layers[0] + 1) * plane, p->buf[b] + plane,
-                                bytes, cudaMemcpyDeviceToDevice, st));
+        TK_CUDA(cudaMemcpyAsync(pptr(p, 0, b, (p->peer_layers[0] + 1) * plane), bptr(p, b, plane), bytes,
+                                cudaMemcpyDeviceToDevice, st));
     if (p->peer_buf[1][b])  // my last owned plane -> upper neighbour's lower halo
-        TK_CUDA(cudaMemcpyAsync(p->peer_buf[1][b], p->buf[b] + plane * p->lat.Lloc, bytes,
+        TK_CUDA(cudaMemcpyAsync(pptr(p, 1, b, 0), bptr(p, b, plane * p->lat.Lloc), bytes,
                                 cudaMemcpyDeviceToDevice, st));
     return TK_OK;
 }
@@ -1186,13 +1293,17 @@ int tk_lattice_signal(tk_plan *p, uint64_t value, void *cuda_stream)
     if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : p->stream;
     const size_t plane = (size_t)p->lat.S * p->lat.S * 4;
+    auto peer_tail = [&](int side) {  // the neighbour's flag block sits after its 256-byte aligned state
+        const size_t bytes = ((size_t)(p->peer_layers[side] + 2) * plane * p->esz + 255) / 256 * 256;
+        return reinterpret_cast<double *>(reinterpret_cast<char *>(p->peer_buf[side][0]) + bytes);
+    };
     if (p->peer_buf[0][0]) {  // lower neighbour's "from above" flag: tail of its buffer 0, word 16
-        double *tail = p->peer_buf[0][0] + (size_t)(p->peer_layers[0] + 2) * plane;
+        double *tail = peer_tail(0);
         const int e = g_write64(st, (unsigned long long)(reinterpret_cast<unsigned long long *>(tail) + 16), value, 0);
         if (e) return fail(TK_ERR_CUDA, "cuStreamWriteValue64 failed with CUresult %d", e);
     }
     if (p->peer_buf[1][0]) {  // upper neighbour's "from below" flag: word 0
-        double *tail = p->peer_buf[1][0] + (size_t)(p->peer_layers[1] + 2) * plane;
+        double *tail = peer_tail(1);
         const int e = g_write64(st, (unsigned long long)reinterpret_cast<unsigned long long *>(tail), value, 0);
         if (e) return fail(TK_ERR_CUDA, "cuStreamWriteValue64 failed with CUresult %d", e);
     }

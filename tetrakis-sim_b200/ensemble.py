@@ -145,6 +145,40 @@ def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, devi
     return EnsembleResult(series, spec_out, arg, freq, eff, clamp, maxdeg, kick_nodes, ms.value, updates)
 
 
+def run_ensemble_sharded(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, *, dist=None,
+                         device: int | None = None, gather: bool = True):
+    """Ensemble spread over the ranks of a ``torch.distributed`` group (one process per GPU): the
+    simulations are independent, so rank r simply runs the contiguous block ``[lo_r, hi_r)`` on its
+    own device -- no data-path communication.  With ``gather=True`` every rank
+    returns the complete :class:`EnsembleResult` (small per-simulation outputs, one all_gather_object);
+    otherwise only its own block plus ``(lo, hi)``."""
+    specs = list(specs)
+    n = len(specs)
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+
+    def part(a):
+        a = np.asarray(a, dtype=np.float64)
+        return a if a.ndim == 0 else a[lo:hi]
+
+    dev = rank if device is None else device
+    mine = run_ensemble(specs[lo:hi], steps, c=part(c), dt=part(dt), damping=part(damping),
+                        kicks=None if kicks is None else kicks[lo:hi], device=dev) if hi > lo else None
+    if not gather or world == 1:
+        return mine, (lo, hi)
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    parts = [p for p in parts if p is not None]
+    cat = lambda f: np.concatenate([getattr(p, f) for p in parts])  # noqa: E731
+    return EnsembleResult(cat("series"), cat("spectrum"), cat("dominant_bin"), cat("dominant_freq"),
+                          cat("effective_dt"), cat("stability_adjusted"), cat("max_degree"),
+                          [k for p in parts for k in p.kick_nodes], max(p.elapsed_ms for p in parts),
+                          sum(p.node_updates for p in parts)), (lo, hi)
+
+
 def sweep_grid(size: int, layers: int, radii, dampings, dts, *, dim: int = 3, defect="blackhole",
                **defect_kw):
     """Specs + per-simulation (damping, dt) arrays for a radius x damping x dt grid (BASELINE config 5).

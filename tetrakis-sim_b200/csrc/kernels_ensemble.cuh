@@ -30,6 +30,13 @@ struct EnsDev {
 
 constexpr int kEnsMaxCorr = 32;
 
+// Shared-memory layout (per CTA = per simulation in flight):
+//   ua, ub        [N]        the two state buffers (u_{t+1} overwrites u_{t-1})
+//   rs, cs        [nline]    masked row / column sums of u_t
+//   series, twc, tws [nt]    probe series, DFT twiddles
+//   lmask         [2*nline]  64-bit participation mask of every row / column line (S <= 64)
+//   meta          [ncell]    per cell: {degree of the 4 nodes (u8 x 4), row line | column line << 16,
+//                            part|alive|part(z-1)|part(z+1) bits}: no index arithmetic in the step loop
 __global__ void __launch_bounds__(448, 2)
 ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
 {
@@ -38,17 +45,18 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
     const int nt = P.steps + 1;
     double *ua = reinterpret_cast<double *>(tk_smem);
     double *ub = ua + N;
-    double *rs = ub + N;        // [L][S][4] row sums
-    double *cs = rs + nline;    // [L][S][4] column sums
-    double *series = cs + nline;  // [nt]
-    double *twc = series + nt;    // [nt] cos(2 pi j / nt)
-    double *tws = twc + nt;       // [nt] sin(2 pi j / nt)
-    double *csig = tws + nt;      // [kEnsMaxCorr]
-    float *rc = reinterpret_cast<float *>(csig + kEnsMaxCorr);  // [nline] row participation counts
-    float *cc = rc + nline;                                     // [nline]
-    int *ca = reinterpret_cast<int *>(cc + nline);              // [kEnsMaxCorr]
+    double *rs = ub + N;
+    double *cs = rs + nline;
+    double *series = cs + nline;
+    double *twc = series + nt;
+    double *tws = twc + nt;
+    double *csig = tws + nt;                                                       // [kEnsMaxCorr]
+    unsigned long long *lmask = reinterpret_cast<unsigned long long *>(csig + kEnsMaxCorr);  // [2*nline]
+    uint4 *meta = reinterpret_cast<uint4 *>(
+        (reinterpret_cast<uintptr_t>(lmask + 2 * nline) + 15) & ~(uintptr_t)15);  // [ncell], 16 B aligned
+    int *ca = reinterpret_cast<int *>(meta + ncell);                               // [kEnsMaxCorr]
     int *cb = ca + kEnsMaxCorr;
-    unsigned char *bits = reinterpret_cast<unsigned char *>(cb + kEnsMaxCorr);  // [ncell]
+    unsigned char *bits = reinterpret_cast<unsigned char *>(cb + kEnsMaxCorr);      // [ncell]
 
     const int tid = threadIdx.x, nth = blockDim.x;
     for (int j = tid; j < nt; j += nth) {
@@ -84,19 +92,43 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
             ua[kick] = P.sim_kick_value[sim];
             series[0] = ua[kick];
         }
-        // static participation counts of every row / column line
+        // participation mask of every row / column line (bit k = k-th cell along the line)
         for (int i = tid; i < 2 * nline; i += nth) {
             const bool is_col = i >= nline;
             const int l = is_col ? i - nline : i;
             const int q = l & 3, x = (l >> 2) % S, z = (l >> 2) / S;
-            int cnt = 0;
+            unsigned long long m = 0ull;
             for (int k = 0; k < S; ++k) {
                 const int cell = is_col ? (z * S + k) * S + x : (z * S + x) * S + k;
-                cnt += (bits[cell] >> q) & 1;
+                m |= (unsigned long long)((bits[cell] >> q) & 1) << k;
             }
-            (is_col ? cc : rc)[l] = (float)cnt;
+            lmask[i] = m;
+        }
+        __syncthreads();
+        // per-cell metadata: degrees (physics.py:60-62 on the clique model), line ids, flag bits
+        for (int cell = tid; cell < ncell; cell += nth) {
+            const int c = cell % S, r = (cell / S) % S, z = cell / (S * S);
+            const unsigned f = bits[cell];
+            const unsigned fm = z > 0 ? bits[cell - S * S] : 0u;
+            const unsigned fp = z < L - 1 ? bits[cell + S * S] : 0u;
+            const int rl = (z * S + r) * 4, cl = (z * S + c) * 4;
+            const int ccnt = __popc(f & 0xFu);
+            unsigned deg4 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int dg = 0;
+                if ((f >> q) & 1u)
+                    dg = (ccnt - 1) + (__popcll(lmask[rl + q]) - 1) + (__popcll(lmask[nline + cl + q]) - 1) +
+                         (int)((fm >> q) & 1u) + (int)((fp >> q) & 1u);
+                for (int k = 0; k < ncorr; ++k)
+                    if (ca[k] == cell * 4 + q) dg += (int)csig[k];
+                deg4 |= (unsigned)(dg & 0xFF) << (8 * q);
+            }
+            meta[cell] = make_uint4(deg4, (unsigned)rl | ((unsigned)cl << 16),
+                                    (f & 0xFFu) | ((fm & 0xFu) << 8) | ((fp & 0xFu) << 12), 0u);
         }
         double *u = ua, *w = ub;
+        const int plane = S * S * 4;
         for (int t = 0; t < P.steps; ++t) {
             __syncthreads();
             // phase A: masked row / column sums of u_t
@@ -104,28 +136,49 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
                 const bool is_col = i >= nline;
                 const int l = is_col ? i - nline : i;
                 const int q = l & 3, x = (l >> 2) % S, z = (l >> 2) / S;
-                double acc = 0.0;
-                for (int k = 0; k < S; ++k) {
-                    const int cell = is_col ? (z * S + k) * S + x : (z * S + x) * S + k;
-                    if ((bits[cell] >> q) & 1) acc += u[cell * 4 + q];
+                const double *p = u + (is_col ? (z * S * S + x) * 4 : (z * S + x) * S * 4) + q;
+                const int stride = is_col ? S * 4 : 4;
+                unsigned long long m = lmask[i];
+                double a0 = 0.0, a1 = 0.0;
+                int k = 0;
+                for (; k + 1 < S; k += 2) {
+                    if (m & 1ull) a0 += p[k * stride];
+                    if (m & 2ull) a1 += p[(k + 1) * stride];
+                    m >>= 2;
                 }
-                (is_col ? cs : rs)[l] = acc;
+                if (k < S && (m & 1ull)) a0 += p[k * stride];
+                (is_col ? cs : rs)[l] = a0 + a1;
             }
             __syncthreads();
             // phase B: update every cell; u_{t+1} overwrites u_{t-1}
             for (int cell = tid; cell < ncell; cell += nth) {
-                const int c = cell % S, r = (cell / S) % S, z = cell / (S * S);
-                const unsigned f = bits[cell];
-                const unsigned fm = z > 0 ? bits[cell - S * S] : 0u;
-                const unsigned fp = z < L - 1 ? bits[cell + S * S] : 0u;
+                const uint4 md = meta[cell];
+                const unsigned f = md.z;
+                const int rl = (int)(md.y & 0xFFFFu), cl = (int)(md.y >> 16);
                 const double2 a = *reinterpret_cast<const double2 *>(u + cell * 4);
                 const double2 b = *reinterpret_cast<const double2 *>(u + cell * 4 + 2);
-                const double uq[4] = {a.x, a.y, b.x, b.y};
+                const double2 wa = *reinterpret_cast<const double2 *>(w + cell * 4);
+                const double2 wb = *reinterpret_cast<const double2 *>(w + cell * 4 + 2);
+                const double2 r0 = *reinterpret_cast<const double2 *>(rs + rl);
+                const double2 r1 = *reinterpret_cast<const double2 *>(rs + rl + 2);
+                const double2 k0 = *reinterpret_cast<const double2 *>(cs + cl);
+                const double2 k1 = *reinterpret_cast<const double2 *>(cs + cl + 2);
+                double2 m0 = make_double2(0.0, 0.0), m1 = m0, p0 = m0, p1 = m0;
+                if (f & 0xF00u) {
+                    m0 = *reinterpret_cast<const double2 *>(u + cell * 4 - plane);
+                    m1 = *reinterpret_cast<const double2 *>(u + cell * 4 - plane + 2);
+                }
+                if (f & 0xF000u) {
+                    p0 = *reinterpret_cast<const double2 *>(u + cell * 4 + plane);
+                    p1 = *reinterpret_cast<const double2 *>(u + cell * 4 + plane + 2);
+                }
+                const double uq[4] = {a.x, a.y, b.x, b.y}, up[4] = {wa.x, wa.y, wb.x, wb.y};
+                const double RS[4] = {r0.x, r0.y, r1.x, r1.y}, CS[4] = {k0.x, k0.y, k1.x, k1.y};
+                const double zm[4] = {m0.x, m0.y, m1.x, m1.y}, zp[4] = {p0.x, p0.y, p1.x, p1.y};
                 double cellsum = 0.0;
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     if ((f >> q) & 1u) cellsum += uq[q];
-                const double ccnt = (double)__popc(f & 0xFu);
                 double un[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -133,21 +186,19 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
                     const bool part = (f >> q) & 1u, alive = (f >> (4 + q)) & 1u;
                     double lap = 0.0;
                     if (part) {
-                        double nsum = (cellsum - uq[q]) + (rs[(z * S + r) * 4 + q] - uq[q]) +
-                                      (cs[(z * S + c) * 4 + q] - uq[q]);
-                        double deg = (ccnt - 1.0) + ((double)rc[(z * S + r) * 4 + q] - 1.0) +
-                                     ((double)cc[(z * S + c) * 4 + q] - 1.0);
-                        if ((fm >> q) & 1u) { nsum += u[node - S * S * 4]; deg += 1.0; }
-                        if ((fp >> q) & 1u) { nsum += u[node + S * S * 4]; deg += 1.0; }
-                        lap = nsum - deg * uq[q];
+                        double nsum = (cellsum - uq[q]) + (RS[q] - uq[q]) + (CS[q] - uq[q]);
+                        if ((f >> (8 + q)) & 1u) nsum += zm[q];
+                        if ((f >> (12 + q)) & 1u) nsum += zp[q];
+                        lap = nsum;
                     }
                     for (int k = 0; k < ncorr; ++k)
-                        if (ca[k] == node) lap += csig[k] * (u[cb[k]] - uq[q]);
+                        if (ca[k] == node) lap += csig[k] * u[cb[k]];
+                    // degree already includes the corrections' +-1
+                    lap -= (double)((md.x >> (8 * q)) & 0xFFu) * uq[q];
                     double im = 1.0, v = 0.0;
                     if (has_attr) { im = gim[node]; v = gv[node]; }
-                    const double up = w[node];
-                    const double rnew = 2.0 * uq[q] - up + (coeff * im) * lap - (coeff * v) * uq[q] -
-                                        damping * (uq[q] - up);
+                    const double rnew = 2.0 * uq[q] - up[q] + (coeff * im) * lap - (coeff * v) * uq[q] -
+                                        damping * (uq[q] - up[q]);
                     un[q] = alive ? rnew : 0.0;
                     if (node == kick) series[t + 1] = un[q];
                 }
@@ -160,7 +211,7 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
         // epilogue: probe series out, |DFT| (reference physics.py:162-163) and argmax (batch.py:205)
         for (int j = tid; j < nt; j += nth) P.series[(size_t)sim * nt + j] = series[j];
         if (P.spectrum) {
-            double *spec = rs;  // row sums are dead now; reuse if large enough, else recompute below
+            double *spec = rs;  // row sums are dead now; reuse when large enough
             const bool fits = nt <= 2 * nline;
             for (int k = tid; k < nt; k += nth) {
                 double re = 0.0, imag = 0.0;
@@ -194,8 +245,10 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
 inline size_t ensemble_smem_bytes(int S, int L, int steps)
 {
     const size_t ncell = (size_t)L * S * S, N = ncell * 4, nline = (size_t)L * S * 4, nt = steps + 1;
-    size_t b = (2 * N + 2 * nline + 3 * nt + kEnsMaxCorr) * sizeof(double);
-    b += 2 * nline * sizeof(float) + 2 * kEnsMaxCorr * sizeof(int) + ncell;
+    size_t b = (2 * N + 2 * nline + 3 * nt + kEnsMaxCorr) * sizeof(double);  // ua ub rs cs series twc tws csig
+    b += 2 * nline * sizeof(unsigned long long);                             // lmask
+    b += ncell * sizeof(uint4);                                              // meta
+    b += 2 * kEnsMaxCorr * sizeof(int) + ncell + 16;                         // ca cb bits + alignment slack
     return (b + 15) & ~(size_t)15;
 }
 

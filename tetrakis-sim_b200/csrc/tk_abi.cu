@@ -806,7 +806,9 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
                                               : lat_occupancy(p->cpl, p->wc, p->minb, halo != 0));
         int best = 16;
         double best_eff = -1.0;
-        for (int rc_ = 16; rc_ <= 256 && rc_ <= std::max<long long>(16, S); ++rc_) {
+        // (cap at 128 rows: longer marches measured slower -- cfg4 512^3: 256 rows 226 GNUPS, 64-128
+        // rows 244 -- CTAs of neighbouring z-groups drift apart and lose the shared z+-1 lines in L2)
+        for (int rc_ = 16; rc_ <= 128 && rc_ <= std::max<long long>(16, S); ++rc_) {
             const long long tiles = ((S + rc_ - 1) / rc_) * nct * nzg;
             const long long waves = (tiles + slots - 1) / slots;
             const double eff = (double)tiles / (double)(waves * slots) * (1.0 / (1.0 + 1.0 / rc_));
@@ -1408,6 +1410,7 @@ int tk_ensemble_run(int device, const tk_ensemble_desc *d, double *probe_series,
     if (rc) return rc;
     const long long S = d->size, L = d->layers, ncell = L * S * S, N = ncell * 4, nt = d->steps + 1;
     TK_REQUIRE(N < (1LL << 24), "lattice too large for an SM-resident ensemble");
+    TK_REQUIRE(S <= 64 && L * S * 4 <= 65535, "ensemble lattices are limited to size <= 64 and layers*size <= 16383");
     const size_t smem = tk::ensemble_smem_bytes((int)S, (int)L, (int)d->steps);
     cudaDeviceProp prop;
     TK_CUDA(cudaGetDeviceProperties(&prop, device));

@@ -150,60 +150,56 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
                 (is_col ? cs : rs)[l] = a0 + a1;
             }
             __syncthreads();
-            // phase B: update every cell; u_{t+1} overwrites u_{t-1}
-            for (int cell = tid; cell < ncell; cell += nth) {
+            // phase B: update; u_{t+1} overwrites u_{t-1}.  One lane per HALF cell (2 quadrants, one
+            // 16-byte LDS.128 per array): the 8 lanes of a quarter warp then read 128 contiguous bytes,
+            // which is bank-conflict free -- a whole 32-byte cell per lane makes every access 2-way
+            // conflicted (ncu: 41 % of the shared wavefronts were replays).  The cell sum needs the
+            // partner lane's pair: one shuffle.
+            for (int hc = tid; hc < 2 * ncell; hc += nth) {
+                const int cell = hc >> 1, h = hc & 1;
                 const uint4 md = meta[cell];
                 const unsigned f = md.z;
                 const int rl = (int)(md.y & 0xFFFFu), cl = (int)(md.y >> 16);
-                const double2 a = *reinterpret_cast<const double2 *>(u + cell * 4);
-                const double2 b = *reinterpret_cast<const double2 *>(u + cell * 4 + 2);
-                const double2 wa = *reinterpret_cast<const double2 *>(w + cell * 4);
-                const double2 wb = *reinterpret_cast<const double2 *>(w + cell * 4 + 2);
-                const double2 r0 = *reinterpret_cast<const double2 *>(rs + rl);
-                const double2 r1 = *reinterpret_cast<const double2 *>(rs + rl + 2);
-                const double2 k0 = *reinterpret_cast<const double2 *>(cs + cl);
-                const double2 k1 = *reinterpret_cast<const double2 *>(cs + cl + 2);
-                double2 m0 = make_double2(0.0, 0.0), m1 = m0, p0 = m0, p1 = m0;
-                if (f & 0xF00u) {
-                    m0 = *reinterpret_cast<const double2 *>(u + cell * 4 - plane);
-                    m1 = *reinterpret_cast<const double2 *>(u + cell * 4 - plane + 2);
-                }
-                if (f & 0xF000u) {
-                    p0 = *reinterpret_cast<const double2 *>(u + cell * 4 + plane);
-                    p1 = *reinterpret_cast<const double2 *>(u + cell * 4 + plane + 2);
-                }
-                const double uq[4] = {a.x, a.y, b.x, b.y}, up[4] = {wa.x, wa.y, wb.x, wb.y};
-                const double RS[4] = {r0.x, r0.y, r1.x, r1.y}, CS[4] = {k0.x, k0.y, k1.x, k1.y};
-                const double zm[4] = {m0.x, m0.y, m1.x, m1.y}, zp[4] = {p0.x, p0.y, p1.x, p1.y};
-                double cellsum = 0.0;
+                const int n0 = cell * 4 + 2 * h;  // first of this lane's two nodes
+                const double2 a = *reinterpret_cast<const double2 *>(u + n0);
+                const double2 wa = *reinterpret_cast<const double2 *>(w + n0);
+                const double2 r0 = *reinterpret_cast<const double2 *>(rs + rl + 2 * h);
+                const double2 k0 = *reinterpret_cast<const double2 *>(cs + cl + 2 * h);
+                double2 m0 = make_double2(0.0, 0.0), p0 = m0;
+                if (f & 0xF00u) m0 = *reinterpret_cast<const double2 *>(u + n0 - plane);
+                if (f & 0xF000u) p0 = *reinterpret_cast<const double2 *>(u + n0 + plane);
+                const double uq[2] = {a.x, a.y}, up[2] = {wa.x, wa.y};
+                const double RS[2] = {r0.x, r0.y}, CS[2] = {k0.x, k0.y};
+                const double zm[2] = {m0.x, m0.y}, zp[2] = {p0.x, p0.y};
+                double mine = 0.0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if ((f >> q) & 1u) cellsum += uq[q];
-                double un[4];
+                for (int j = 0; j < 2; ++j)
+                    if ((f >> (2 * h + j)) & 1u) mine += uq[j];
+                const double other = __shfl_xor_sync(__activemask(), mine, 1);
+                const double cellsum = h ? other + mine : mine + other;  // same order in both lanes
+                double un[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int node = cell * 4 + q;
+                for (int j = 0; j < 2; ++j) {
+                    const int q = 2 * h + j, node = n0 + j;
                     const bool part = (f >> q) & 1u, alive = (f >> (4 + q)) & 1u;
                     double lap = 0.0;
                     if (part) {
-                        double nsum = (cellsum - uq[q]) + (RS[q] - uq[q]) + (CS[q] - uq[q]);
-                        if ((f >> (8 + q)) & 1u) nsum += zm[q];
-                        if ((f >> (12 + q)) & 1u) nsum += zp[q];
+                        double nsum = (cellsum - uq[j]) + (RS[j] - uq[j]) + (CS[j] - uq[j]);
+                        if ((f >> (8 + q)) & 1u) nsum += zm[j];
+                        if ((f >> (12 + q)) & 1u) nsum += zp[j];
                         lap = nsum;
                     }
                     for (int k = 0; k < ncorr; ++k)
                         if (ca[k] == node) lap += csig[k] * u[cb[k]];
-                    // degree already includes the corrections' +-1
-                    lap -= (double)((md.x >> (8 * q)) & 0xFFu) * uq[q];
+                    lap -= (double)((md.x >> (8 * q)) & 0xFFu) * uq[j];  // degree incl. corrections
                     double im = 1.0, v = 0.0;
                     if (has_attr) { im = gim[node]; v = gv[node]; }
-                    const double rnew = 2.0 * uq[q] - up[q] + (coeff * im) * lap - (coeff * v) * uq[q] -
-                                        damping * (uq[q] - up[q]);
-                    un[q] = alive ? rnew : 0.0;
-                    if (node == kick) series[t + 1] = un[q];
+                    const double rnew = 2.0 * uq[j] - up[j] + (coeff * im) * lap - (coeff * v) * uq[j] -
+                                        damping * (uq[j] - up[j]);
+                    un[j] = alive ? rnew : 0.0;
+                    if (node == kick) series[t + 1] = un[j];
                 }
-                *reinterpret_cast<double2 *>(w + cell * 4) = make_double2(un[0], un[1]);
-                *reinterpret_cast<double2 *>(w + cell * 4 + 2) = make_double2(un[2], un[3]);
+                *reinterpret_cast<double2 *>(w + n0) = make_double2(un[0], un[1]);
             }
             double *tmp = u; u = w; w = tmp;
         }

@@ -1497,9 +1497,10 @@ int tk_ensemble_run(int device, const tk_ensemble_desc *d, double *probe_series,
 #define TK_ENS_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); \
         return fail(TK_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while (0)
     TK_ENS_CUDA(cudaFuncSetAttribute(tk::ensemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // threads: whole iterations over the cells, at most 448 per CTA
-    const long long iters = (ncell + 447) / 448;
-    int threads = (int)(((ncell + iters - 1) / iters + 31) / 32 * 32);
+    // threads: whole iterations over the half cells (one lane per 2 quadrants), at most 448 per CTA
+    const long long work = 2 * ncell;
+    const long long iters = (work + 447) / 448;
+    int threads = (int)(((work + iters - 1) / iters + 31) / 32 * 32);
     threads = std::max(64, std::min(threads, 448));
     int occ = 1;
     TK_ENS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk::ensemble_kernel, threads, smem));

@@ -23,17 +23,20 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("cpl", [2, 1])
 @pytest.mark.parametrize("case", list(CASES))
 @pytest.mark.parametrize("steps,tol", [(100, 2e-6), (1000, 2e-5)])
-def test_fp32_mode_tracks_fp64_within_the_stated_tolerance(case, steps, tol):
+def test_fp32_mode_tracks_fp64_within_the_stated_tolerance(case, steps, tol, cpl, monkeypatch):
+    monkeypatch.setenv("TK_LAT_CPL", str(cpl))  # cells per lane of the fp32 kernel (fp64 run: default tiling)
     kw, damping = CASES[case]
     spec = tk.LatticeSpec(**kw)
     kick = spec.kick_node()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
-        h64 = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, dt=0.05, damping=damping)
         h32 = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, dt=0.05, damping=damping,
                               dtype="float32")
+        monkeypatch.delenv("TK_LAT_CPL")
+        h64 = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, dt=0.05, damping=damping)
     assert h32.dt == h64.dt and h32.metadata["max_degree"] == h64.metadata["max_degree"]
     assert rel_inf(h32.final_state, h64.final_state) < tol
     assert rel_inf(h32.probe_series, h64.probe_series) < tol

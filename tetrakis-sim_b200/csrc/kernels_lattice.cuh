@@ -338,13 +338,14 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
 // rounding of the state itself.  One cell per lane (16-byte LDG/STG.128), same tiling, same partial
 // sum layout, same defect tables, same peer halo push as the fp64 kernel.  Tolerance: see
 // tests/test_gpu_fp32.py (documented in DESIGN.md).
-template <int WC, bool K3D, int MODE, int MINB>
+template <int CPL, int WC, bool K3D, int MODE, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 lat_step_f32_kernel(const __grid_constant__ LatDev P, const float *__restrict__ u,
                     float *__restrict__ w, double *__restrict__ prow, double *__restrict__ pcol,
                     double coeff, double damping, int zl_begin, int zl_end, int rchunk, int nchunk,
                     int nsegk, int nct, int nzg, int pf_rows)
 {
+    static_assert(CPL == 1 || CPL == 2, "fp32 kernel: 1 or 2 cells per lane");
     constexpr int WZ = 8 / WC;
     constexpr bool STEP = MODE != 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -358,8 +359,11 @@ lat_step_f32_kernel(const __grid_constant__ LatDev P, const float *__restrict__ 
     if (zl >= zl_end || segk >= nsegk) return;
 
     const int S = P.S;
-    const int c0 = segk * 32 + lane;
-    const bool valid = c0 < S;
+    const int c0 = (segk * 32 + lane) * CPL;
+    bool valid[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) valid[j] = (c0 + j) < S;
+    const bool both = CPL == 2 && valid[CPL - 1];  // the lane's cells are contiguous: one 256-bit access
     const size_t plane = (size_t)S * S * 4;
     const size_t zbase = (size_t)(zl + P.halo) * plane;
     const unsigned fplain = plain_flags(P, zl);
@@ -368,15 +372,20 @@ lat_step_f32_kernel(const __grid_constant__ LatDev P, const float *__restrict__ 
     const float coeff_f = (float)coeff, damp_f = (float)damping;
     float *peer_lo = reinterpret_cast<float *>(P.peer_lo), *peer_hi = reinterpret_cast<float *>(P.peer_hi);
 
-    double CS[4] = {0, 0, 0, 0}, CC[4] = {0, 0, 0, 0}, cacc[4] = {0, 0, 0, 0};
-    if (STEP && valid) {
-        ld256_nc(P.colinfo + ((size_t)zl * S + c0) * 8, CS);
-        ld256_nc(P.colinfo + ((size_t)zl * S + c0) * 8 + 4, CC);
+    double CS[CPL][4], CC[CPL][4], cacc[CPL][4];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { CS[j][q] = 0.0; CC[j][q] = 0.0; cacc[j][q] = 0.0; }
+        if (STEP && valid[j]) {
+            ld256_nc(P.colinfo + ((size_t)zl * S + c0 + j) * 8, CS[j]);
+            ld256_nc(P.colinfo + ((size_t)zl * S + c0 + j) * 8 + 4, CC[j]);
+        }
     }
     const int r_begin = ch * rchunk;
     const int r_end = min(S, r_begin + rchunk);
     const int tab0 = c0 / kTabSeg;
-    const bool pf_lane = STEP && pf_rows > 0 && valid && (lane & 7) == 0;  // one request per 128 B
+    const bool pf_lane = STEP && pf_rows > 0 && valid[0] && ((lane * CPL) & 7) == 0;  // one per 128 B
     if (pf_lane) {
         for (int r = r_begin; r < min(r_end, r_begin + pf_rows); ++r) {
             const size_t o = zbase + ((size_t)r * S + c0) * 4;
@@ -384,6 +393,20 @@ lat_step_f32_kernel(const __grid_constant__ LatDev P, const float *__restrict__ 
             prefetch_l2(w + o);
         }
     }
+    // rows of odd length can leave a lane's second cell misaligned for a 256-bit access
+    const bool wide_ok = CPL == 2 && (S & 1) == 0;
+    auto load = [&](const float *base, float v[CPL * 4], bool streaming) {
+        if (CPL == 2 && both && wide_ok) {
+            if (streaming) ld256f_cs(base, v); else ld256f_nc(base, v);
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[j]) t = streaming ? ld128_cs(base + j * 4) : ld128_nc(base + j * 4);
+            v[j * 4 + 0] = t.x; v[j * 4 + 1] = t.y; v[j * 4 + 2] = t.z; v[j * 4 + 3] = t.w;
+        }
+    };
     for (int r = r_begin; r < r_end; ++r) {
         const size_t rowoff = zbase + ((size_t)r * S + c0) * 4;
         if (pf_lane && r + pf_rows < r_end) {
@@ -391,71 +414,93 @@ lat_step_f32_kernel(const __grid_constant__ LatDev P, const float *__restrict__ 
             prefetch_l2(u + o);
             prefetch_l2(w + o);
         }
-        float4 uq = make_float4(0.f, 0.f, 0.f, 0.f), upq = uq, zm = uq, zp = uq;
-        if (valid) {
-            uq = ld128_nc(u + rowoff);
-            if (STEP) {
-                upq = ld128_cs(w + rowoff);
-                if (zm_on) zm = ld128_nc(u + rowoff - plane);
-                if (zp_on) zp = ld128_nc(u + rowoff + plane);
-            }
+        float uf[CPL * 4], upf[CPL * 4], zmf[CPL * 4], zpf[CPL * 4];
+#pragma unroll
+        for (int i = 0; i < CPL * 4; ++i) { upf[i] = 0.f; zmf[i] = 0.f; zpf[i] = 0.f; }
+        load(u + rowoff, uf, false);
+        if (STEP) {
+            load(w + rowoff, upf, true);
+            if (zm_on) load(u + rowoff - plane, zmf, false);
+            if (zp_on) load(u + rowoff + plane, zpf, false);
         }
         int det = -1;
-        if (valid) det = P.seg_flag[((size_t)zl * S + r) * P.ntab + tab0];
+        if (valid[0]) det = P.seg_flag[((size_t)zl * S + r) * P.ntab + tab0];
         const bool all_plain = __all_sync(0xffffffffu, det < 0);
         double RS[4] = {0, 0, 0, 0}, RC[4] = {0, 0, 0, 0};
         if (STEP) {
             ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8, RS);
             ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8 + 4, RC);
         }
-        const float uf[4] = {uq.x, uq.y, uq.z, uq.w}, upf[4] = {upq.x, upq.y, upq.z, upq.w};
-        const float zmf[4] = {zm.x, zm.y, zm.z, zm.w}, zpf[4] = {zp.x, zp.y, zp.z, zp.w};
-        float un[4];
-        double pun[4];
-        if (MODE == 1) {
-            unsigned f = fplain;
-            if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + (c0 & (kTabSeg - 1))];
-            if (!valid) f = 0;
+        float un[CPL * 4];
+        double rsum[4] = {0, 0, 0, 0};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pun[q] = ((f >> q) & 1u) ? (double)uf[q] : 0.0;
-        } else if (all_plain) {
-            const double cell = (double)((uf[0] + uf[1]) + (uf[2] + uf[3]));
+        for (int j = 0; j < CPL; ++j) {
+            double pun[4];
+            if (MODE == 1) {
+                unsigned f = fplain;
+                if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + ((c0 + j) & (kTabSeg - 1))];
+                if (!valid[j]) f = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const double zz = K3D ? (double)(zmf[q] + zpf[q]) : 0.0;
-                const double nb = (cell + RS[q]) + (CS[q] + zz);
-                const double dg = (RC[q] + degbase) + CC[q];
-                const float lap = (float)(nb - dg * (double)uf[q]);
-                un[q] = 2.0f * uf[q] - upf[q] + coeff_f * lap - damp_f * (uf[q] - upf[q]);
-                pun[q] = valid ? (double)un[q] : 0.0;
+                for (int q = 0; q < 4; ++q) pun[q] = ((f >> q) & 1u) ? (double)uf[j * 4 + q] : 0.0;
+            } else if (all_plain) {
+                const double cell = (double)((uf[j * 4] + uf[j * 4 + 1]) + (uf[j * 4 + 2] + uf[j * 4 + 3]));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float x = uf[j * 4 + q], xp = upf[j * 4 + q];
+                    const double zz = K3D ? (double)(zmf[j * 4 + q] + zpf[j * 4 + q]) : 0.0;
+                    const double nb = (cell + RS[q]) + (CS[j][q] + zz);
+                    const double dg = (RC[q] + degbase) + CC[j][q];
+                    const float lap = (float)(nb - dg * (double)x);
+                    un[j * 4 + q] = 2.0f * x - xp + coeff_f * lap - damp_f * (x - xp);
+                    pun[q] = valid[j] ? (double)un[j * 4 + q] : 0.0;
+                }
+            } else {
+                unsigned f = fplain;
+                if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + ((c0 + j) & (kTabSeg - 1))];
+                if (!valid[j]) f = 0;
+                CellIO io;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    io.uq[q] = uf[j * 4 + q]; io.upq[q] = upf[j * 4 + q];
+                    io.zm[q] = zmf[j * 4 + q]; io.zp[q] = zpf[j * 4 + q];
+                    io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[j][q]; io.CC[q] = CC[j][q];
+                }
+                cell_update_detail_f32(P, u, det, (c0 + j) & (kTabSeg - 1), (long long)(rowoff + j * 4), f,
+                                       coeff, damping, io);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    un[j * 4 + q] = (float)io.un[q];
+                    pun[q] = ((f >> q) & 1u) ? (double)un[j * 4 + q] : 0.0;
+                }
             }
-        } else {
-            unsigned f = fplain;
-            if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + (c0 & (kTabSeg - 1))];
-            if (!valid) f = 0;
-            CellIO io;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                io.uq[q] = uf[q]; io.upq[q] = upf[q]; io.zm[q] = zmf[q]; io.zp[q] = zpf[q];
-                io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[q]; io.CC[q] = CC[q];
-            }
-            cell_update_detail_f32(P, u, det, c0 & (kTabSeg - 1), (long long)rowoff, f, coeff, damping, io);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { un[q] = (float)io.un[q]; pun[q] = ((f >> q) & 1u) ? (double)un[q] : 0.0; }
+            for (int q = 0; q < 4; ++q) { cacc[j][q] += pun[q]; rsum[q] += pun[q]; }
         }
-        if (STEP && valid) {
-            const float4 v = make_float4(un[0], un[1], un[2], un[3]);
-            st128_cs(w + rowoff, v);
-            if (K3D) {
-                if (zl == 0 && peer_lo) st128(peer_lo + (rowoff - zbase), v);
-                if (zl == P.Lloc - 1 && peer_hi) st128(peer_hi + (rowoff - zbase), v);
+        if (STEP) {
+            if (CPL == 2 && both && wide_ok) {
+                st256f_cs(w + rowoff, un);
+                if (K3D) {
+                    if (zl == 0 && peer_lo) st256f(peer_lo + (rowoff - zbase), un);
+                    if (zl == P.Lloc - 1 && peer_hi) st256f(peer_hi + (rowoff - zbase), un);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    if (valid[j]) {
+                        const float4 v = make_float4(un[j * 4], un[j * 4 + 1], un[j * 4 + 2], un[j * 4 + 3]);
+                        st128_cs(w + rowoff + j * 4, v);
+                        if (K3D) {
+                            if (zl == 0 && peer_lo) st128(peer_lo + (rowoff - zbase) + j * 4, v);
+                            if (zl == P.Lloc - 1 && peer_hi) st128(peer_hi + (rowoff - zbase) + j * 4, v);
+                        }
+                    }
             }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) cacc[q] += pun[q];
-        warp_sum4_store(pun, lane, prow + (((size_t)zl * S + r) * nsegk + segk) * 4);
+        warp_sum4_store(rsum, lane, prow + (((size_t)zl * S + r) * nsegk + segk) * 4);
     }
-    if (valid) st256(pcol + (((size_t)zl * nchunk + ch) * S + c0) * 4, cacc);
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+        if (valid[j]) st256(pcol + (((size_t)zl * nchunk + ch) * S + c0 + j) * 4, cacc[j]);
 }
 
 // 3-D step with explicit on-chip sharing of the z neighbours (cp.async multi-stage pipeline).

@@ -204,11 +204,12 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
         p->lat.peer_hi = p->peer_buf[1][nb] ? p->peer_buf[1][nb] : nullptr;
     }
     if (is_f32(p)) {
-        if (CPL != 1 || MODE == 2)
-            return fail(TK_ERR_INVALID, "fp32 plans support cells_per_lane = 1 and no energy series");
-        constexpr int FM = (CPL == 1 && MODE != 2) ? MODE : 0;
-        constexpr int FB = (MINB >= 2 && MINB <= 4) ? MINB : 3;
-        tk::lat_step_f32_kernel<WC, K3D, FM, FB><<<(unsigned)grid, 256, 0, st>>>(
+        if (CPL > 2 || MODE == 2)
+            return fail(TK_ERR_INVALID, "fp32 plans support 1 or 2 cells per lane and no energy series");
+        constexpr int FC = CPL <= 2 ? CPL : 1;
+        constexpr int FM = MODE != 2 ? MODE : 0;
+        constexpr int FB = (MINB >= 1 && MINB <= 4) ? MINB : 3;
+        tk::lat_step_f32_kernel<FC, WC, K3D, FM, FB><<<(unsigned)grid, 256, 0, st>>>(
             p->lat, reinterpret_cast<const float *>(p->buf[p->cur]), reinterpret_cast<float *>(p->buf[p->cur ^ 1]),
             p->prow, p->pcol, p->coeff, p->damping, zl_begin, zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg,
             p->pf_rows);
@@ -779,10 +780,11 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
     p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? (halo ? 2 : 3) : 1);
     p->pf_rows = env_int("TK_LAT_PREFETCH", halo ? 2 : 1);
     if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 1; p->wc = halo ? 1 : 8; p->minb = 3; }
-    if (p->esz == 4) {  // fp32: one cell per lane, 2-3 CTAs/SM; the staged 3-D kernel is fp64-only
-        p->cpl = 1;
-        if (p->minb < 2 || p->minb > 4) p->minb = 3;
-        if (!lat_supported(p->cpl, p->wc, p->minb)) { p->wc = halo ? 1 : 8; p->minb = halo ? 2 : 3; }
+    if (p->esz == 4) {  // fp32: 2 cells (32 B) per lane by default; the staged 3-D kernel is fp64-only
+        p->cpl = env_int("TK_LAT_CPL", 2);
+        if (p->cpl != 1 && p->cpl != 2) p->cpl = 2;
+        p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? 3 : 2);
+        if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 2; p->wc = halo ? 1 : 8; p->minb = 2; }
     }
     if (halo && p->esz == 8 && env_int("TK_LAT3D", 0)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
         p->wz3d = env_int("TK_LAT3D_WZ", 8);

@@ -780,11 +780,11 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
     p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? (halo ? 2 : 3) : 1);
     p->pf_rows = env_int("TK_LAT_PREFETCH", halo ? 2 : 1);
     if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 1; p->wc = halo ? 1 : 8; p->minb = 3; }
-    if (p->esz == 4) {  // fp32: 2 cells (32 B) per lane by default; the staged 3-D kernel is fp64-only
-        p->cpl = env_int("TK_LAT_CPL", 2);
-        if (p->cpl != 1 && p->cpl != 2) p->cpl = 2;
+    if (p->esz == 4) {  // fp32 (sweep, profiles/r01_sweeps.md): 2-D 2 cells per lane, 3-D 1 cell per lane
+        p->cpl = env_int("TK_LAT_CPL", halo ? 1 : 2);
+        if (p->cpl != 1 && p->cpl != 2) p->cpl = halo ? 1 : 2;
         p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? 3 : 2);
-        if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 2; p->wc = halo ? 1 : 8; p->minb = 2; }
+        if (!lat_supported(p->cpl, p->wc, p->minb)) { p->cpl = 1; p->wc = halo ? 1 : 8; p->minb = 3; }
     }
     if (halo && p->esz == 8 && env_int("TK_LAT3D", 0)) {  // 3-D: shared-memory staged kernel (1 cell per lane)
         p->wz3d = env_int("TK_LAT3D_WZ", 8);

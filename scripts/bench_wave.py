@@ -5,7 +5,7 @@ Same flags and the same CSV (header and column meaning, reference scripts/bench_
 ``dim,layers,size,steps,repeats,nodes,edges,max_degree,build_s,sim_s_median,sim_s_min,sim_s_max,
 effective_dt,stability_adjusted``.  ``build_s`` is the graph-to-device compile, ``sim_s_*`` the wall
 time of ``run_wave_sim`` (kick ``(size//2, size//2[, layers//2], "A")``, bench_wave.py:43-46).
-``--path graph`` builds the networkx graph with the oracle's builder and runs the bit-exact sliced-ELL
+``--path graph`` builds the networkx graph (``LatticeSpec.to_networkx``) and runs the bit-exact sliced-ELL
 kernel (sizes networkx can hold); the default ``--path spec`` uses a LatticeSpec and scales to any size.
 ``--gnups`` appends node-updates/s columns.
 """
@@ -38,9 +38,7 @@ def bench_one(size, dim, layers, steps, c, dt, damping, repeats, path):
     kick = spec.bench_kick_node()
     t0 = time.perf_counter()
     if path == "graph":
-        from oracle import lattice_oracle as lo  # test infrastructure: only used to obtain a graph
-
-        target = lo.build_sheet(size=size, dim=dim, layers=layers)
+        target = spec.to_networkx()
     else:
         target = spec
     build_s = time.perf_counter() - t0

@@ -183,3 +183,17 @@ def test_sweep_grid_ordering():
     specs, damp, dt = tk.sweep_grid(13, 7, [0.5, 4.0], [0.0, 0.05, 0.1], [0.02, 0.2])
     assert len(specs) == 12 and specs[0] is specs[5] and specs[6].radius == 4.0
     assert damp.tolist() == [0.0, 0.0, 0.05, 0.05, 0.1, 0.1] * 2 and dt.tolist() == [0.02, 0.2] * 6
+
+
+@pytest.mark.parametrize("name", lattice_names())
+def test_lattice_spec_to_networkx_is_the_reference_graph(name):
+    """Node order, adjacency ORDER and attributes of LatticeSpec.to_networkx() equal the reference's."""
+    g = load_golden(name)
+    if len(g["nodes"]) > 3500:
+        pytest.skip("covered by the smaller cases")
+    G = _spec_from(g["lattice"]).to_networkx()
+    nodes, index, rowptr, colidx, degree, inv_mass, potential = graph_arrays(G)
+    enc = np.array([[*n[:-1], "ABCD".index(n[-1])] for n in nodes], dtype=np.int64)
+    assert np.array_equal(enc, g["nodes"])
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(colidx, g["colidx"])
+    assert np.array_equal(inv_mass, g["inv_mass"]) and np.array_equal(potential, g["potential"])

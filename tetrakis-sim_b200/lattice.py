@@ -275,6 +275,61 @@ class LatticeSpec:
         s = self.size // 2
         return (s, s, "A") if self.dim == 2 else (s, s, self.layers // 2, "A")
 
+    def to_networkx(self):
+        """The lattice + defect as a ``networkx`` graph, for sizes networkx can hold (plotting,
+        curvature and the other graph consumers of the reference keep working).  Node order, adjacency
+        order and attributes are those of ``apply_defect(build_sheet(...))``: edges are inserted layer
+        by layer as cell cliques, row cliques, column cliques, then the vertical links
+        (lattice.py:37-44, 58-72) -- skipping what the defect removed, which leaves the same relative
+        order as removing it afterwards."""
+        import networkx as nx
+        from itertools import combinations
+
+        S, L = self.size, self.layers
+        idx, flags, im, pot = self.specials()
+        dead = set(idx[(flags & FLAG_ALIVE) == 0].tolist())
+        loose = set(idx[(flags & FLAG_PART) == 0].tolist()) | dead  # nodes without any edge
+        cut = {(a, b) for a, b, _ in self.corrections()}
+
+        def nid(z, r, c, q):
+            return ((z * S + r) * S + c) * 4 + q
+
+        def label(i):
+            return self.node(i)
+
+        G = nx.Graph()
+        order = (nid(z, r, c, q) for r in range(S) for c in range(S) for z in range(L) for q in range(4))
+        G.add_nodes_from(label(i) for i in order if i not in dead)
+
+        def link(a, b):
+            if a not in loose and b not in loose and (a, b) not in cut:
+                G.add_edge(label(a), label(b))
+
+        for z in range(L):
+            for r in range(S):
+                for c in range(S):
+                    for qa, qb in combinations(range(4), 2):
+                        link(nid(z, r, c, qa), nid(z, r, c, qb))
+            for r in range(S):
+                for q in range(4):
+                    for ca, cb in combinations(range(S), 2):
+                        link(nid(z, r, ca, q), nid(z, r, cb, q))
+            for c in range(S):
+                for q in range(4):
+                    for ra, rb in combinations(range(S), 2):
+                        link(nid(z, ra, c, q), nid(z, rb, c, q))
+        for z in range(L - 1):
+            for r in range(S):
+                for c in range(S):
+                    for q in range(4):
+                        link(nid(z, r, c, q), nid(z + 1, r, c, q))
+        if self.defect == "singularity":
+            for i in idx.tolist():
+                if i not in dead:
+                    G.nodes[label(i)].update(mass=float(self.mass), potential=float(self.potential),
+                                             singular=True)
+        return G
+
     def slab(self, rank: int, world: int) -> tuple[int, int]:
         """Contiguous block of layers owned by ``rank`` of ``world``."""
         base, extra = divmod(self.layers, world)

@@ -248,7 +248,37 @@ def cli_goldens():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def cfg5_spotcheck():
+    """64 random points (seed 0) of the radius x damping x dt grid of
+    65 536 simulations (size 13, layers 7, 50 steps), run through the unmodified reference."""
+    radii, dampings, dts = np.linspace(0.5, 4.0, 64), np.linspace(0.0, 0.05, 32), np.linspace(0.02, 0.2, 32)
+    rng = np.random.default_rng(0)
+    picks = np.sort(rng.choice(64 * 32 * 32, 64, replace=False))
+    series, spectra, eff, kicks = [], [], [], []
+    for g in picks:
+        ir, idamp, idt = g // 1024, (g // 32) % 32, g % 32
+        G = build_sheet(size=13, dim=3, layers=7)
+        center = (6, 6, 3)
+        G, _ = apply_defect(G, defect_type="blackhole", return_removed=True, center=center, radius=float(radii[ir]))
+        k = kick_rule(G, center, 3)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            h = run_wave_sim(G, steps=50, initial_data={k: 1.0}, c=1.0, dt=float(dts[idt]), damping=float(dampings[idamp]))
+        f, sp, v = run_fft(h, k)
+        series.append(v)
+        spectra.append(sp)
+        eff.append(h.dt)
+        kicks.append([*k[:-1], "ABCD".index(k[-1])])
+    np.savez_compressed(os.path.join(HERE, "cfg5_spotcheck.npz"), picks=picks, series=np.array(series),
+                        spectra=np.array(spectra), effective_dt=np.array(eff), kicks=np.array(kicks))
+    print("cfg5 spot-check golden:", len(picks), "grid points")
+
+
 if __name__ == "__main__":
+    if "--cfg5-only" in sys.argv:
+        cfg5_spotcheck()
+        sys.exit(0)
     if "--cli-only" not in sys.argv:
         main()
+        cfg5_spotcheck()
     cli_goldens()

@@ -63,3 +63,26 @@ def test_ensemble_argument_errors():
                         kicks=[(3, 3, "A")])
     with pytest.raises(ValueError, match="shared memory"):
         tk.run_ensemble([tk.LatticeSpec(size=64, dim=3, layers=8)], 5)
+
+
+def test_config5_grid_spot_check_against_the_reference():
+    """64 random points (seed 0) of BASELINE config 5's 64 x 32 x 32 grid, each run
+    through the unmodified reference (tests/golden/cfg5_spotcheck.npz) vs the ensemble kernel running
+    the WHOLE 65 536-member grid in one launch."""
+    import os
+
+    from tests.helpers import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, "cfg5_spotcheck.npz"))
+    radii, dampings, dts = np.linspace(0.5, 4.0, 64), np.linspace(0.0, 0.05, 32), np.linspace(0.02, 0.2, 32)
+    specs, damp, dt = tk.sweep_grid(13, 7, radii, dampings, dts)
+    res = tk.run_ensemble(specs, 50, c=1.0, dt=dt, damping=damp)
+    assert res.series.shape == (65536, 51)
+    picks = z["picks"]
+    assert np.array_equal(res.effective_dt[picks], z["effective_dt"])
+    for i, g in enumerate(picks):
+        k = res.kick_nodes[g]
+        assert [*k[:-1], "ABCD".index(k[-1])] == z["kicks"][i].tolist()
+        assert rel_inf(res.series[g], z["series"][i]) < 1e-12
+        assert rel_inf(res.spectrum[g], z["spectra"][i]) < 1e-11
+        assert wo.folded_bin(res.spectrum[g]) == wo.folded_bin(z["spectra"][i])

@@ -320,3 +320,49 @@ def test_run_fft_many_equals_per_node_run_fft():
         assert np.array_equal(f1, freq) and np.array_equal(v1, values[i]) and np.array_equal(s1, spectra[i])
         assert bins[i] == int(np.argmax(s1))
     assert rel_inf(spectra, np.abs(np.fft.fft(values, axis=1))) < 1e-12
+
+
+def test_medium_2d_lattice_against_the_c_oracle():
+    """SURVEY.md 8d config 2 at reduced size: 2-D 2048 x 2048 (16.8 M nodes, 32 kernel segments per row,
+    many row chunks) against the CPU clique-sum oracle."""
+    spec = tk.LatticeSpec(size=2048, dim=2)
+    kick = spec.bench_kick_node()
+    steps = 30
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        h = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, c=1.0, dt=0.1, probes=[kick, (0, 2047, "D")])
+    u0 = np.zeros(spec.num_slots)
+    u0[spec.index(kick)] = 1.0
+    ref = wo.run_structured(2048, 1, None, None, None, [], u0, steps, (1.0 * h.dt) ** 2, 0.0,
+                            probes=[spec.index(kick), spec.index((0, 2047, "D"))])
+    assert h.metadata["max_degree"] == 3 + 2 * 2047 and h.metadata["stability_adjusted"] is True
+    assert rel_inf(h.final_state, ref["u"]) < 1e-12
+    assert rel_inf(h.probe_series, ref["probes"]) < 1e-12
+
+
+def test_ten_thousand_steps_against_the_bit_exact_oracle():
+    """BASELINE north_star: relative 1e-10 on u(t) after N steps, N = 10 000 (config 2's step count).
+    Truth = the generic C oracle, which is bit-identical to the reference (tests/test_oracle_golden.py);
+    rounding differences between the reference's neighbour-order sums and the clique sums grow ~N^2
+    (2.3e-11 at 5 000 steps is the reference's own float64 noise floor)."""
+    from oracle import lattice_oracle as lo
+
+    G = lo.build_sheet(size=15, dim=2)
+    kick = (7, 7, "A")
+    nodes, rowptr, colidx, inv_mass, potential = lo.graph_arrays(G)
+    deg = np.array([G.degree[n] for n in nodes], dtype=np.float64)
+    u0 = np.zeros(len(nodes))
+    u0[nodes.index(kick)] = 1.0
+    steps, dt = 10_000, 0.1
+    truth = wo.run_graph(rowptr, colidx, deg, inv_mass, potential, u0, steps, dt * dt, 0.0,
+                         probes=[nodes.index(kick)], keep_history=False)
+    hg = tk.run_wave_sim(G, steps=steps, initial_data={kick: 1.0}, dt=dt, record="probes")
+    assert np.array_equal(hg.final_state, truth["u"]), "graph kernel must stay bit-exact at 10k steps"
+    assert np.array_equal(hg.probe_series[:, 0], truth["probes"][:, 0])
+    spec = tk.LatticeSpec(size=15, dim=2)
+    hs = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, dt=dt)
+    idx = np.array([spec.index(n) for n in nodes])
+    err = rel_inf(hs.final_state[idx], truth["u"])
+    err_t = np.max(np.abs(hs.probe_series[:, 0] - truth["probes"][:, 0])) / np.max(np.abs(truth["probes"]))
+    print(f"10k-step structured-vs-reference error: final {err:.2e}, probe series {err_t:.2e}")
+    assert err < 1e-10 and err_t < 1e-10

@@ -132,6 +132,13 @@ typedef struct tk_run_args {
  * consecutive calls continue the same simulation. */
 int tk_plan_run(tk_plan *plan, const tk_run_args *args);
 
+/* Probe recording for phase-driven runs (tk_lattice_step_*): the next `rows` finalise calls (one in
+ * tk_lattice_step_begin, one per tk_lattice_step_end) each record the probes' values.  tk_plan_run
+ * manages its own probes and overrides this. */
+int tk_plan_set_probes(tk_plan *plan, int64_t n_probes, const int64_t *probe_index, int64_t rows);
+/* Copy the rows recorded so far (rows_recorded x n_probes doubles) to the host; synchronises. */
+int tk_plan_read_probes(tk_plan *plan, double *out, int64_t *rows_recorded);
+
 /* Kernel launches issued by this plan since creation (bench.py's gpu_launches). */
 int tk_plan_launch_count(const tk_plan *plan, int64_t *launches);
 int tk_plan_destroy(tk_plan *plan);

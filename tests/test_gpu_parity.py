@@ -366,3 +366,36 @@ def test_ten_thousand_steps_against_the_bit_exact_oracle():
     err_t = np.max(np.abs(hs.probe_series[:, 0] - truth["probes"][:, 0])) / np.max(np.abs(truth["probes"]))
     print(f"10k-step structured-vs-reference error: final {err:.2e}, probe series {err_t:.2e}")
     assert err < 1e-10 and err_t < 1e-10
+
+
+def test_full_config3_on_one_gpu_uses_64_bit_indexing():
+    """BASELINE config 3 whole (1024 x 1024 x 512 = 2^31 node slots, 34 GB of state) on ONE device: the
+    kick and a probe sit in the top layer (linear index > INT32_MAX), and the device-side checksum
+    sum_i u_t(i) = sum(u_0) (1 + t) covers every node."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~40 GB of free device memory")
+    spec = tk.LatticeSpec(size=1024, dim=3, layers=512, defect="blackhole", radius=64.0)
+    assert spec.num_slots == 2**31
+    top, mid = (512, 515, 511, "C"), spec.kick_node()
+    assert spec.index(top) > 2**31 - 2**22 > np.iinfo(np.int32).max - 2**22
+    plan = tk.compile_lattice(spec)
+    try:
+        assert plan.max_degree == 3 + 2 * 1023 + 2
+        plan.set_state_sparse([spec.index(top), spec.index(mid)], [-0.75, 1.0])
+        steps = 6
+        out = plan.run(steps, 0.0221**2, 0.0, probes=[spec.index(top), spec.index(mid), spec.index((512, 515, 510, "C"))])
+        assert out["probes"][0].tolist() == [-0.75, 1.0, 0.0]
+        assert abs(out["probes"][-1, 0]) > 0.1 and out["probes"][1, 2] != 0.0  # the layer below the kick moved
+
+        class Raw:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        n_all = (spec.layers + 2) * spec.plane
+        sums = [float(torch.as_tensor(Raw(p, n_all), device="cuda:0").sum().item()) for p in plan.state_ptrs()]
+        assert any(abs(s - 0.25 * (1 + steps)) < 1e-10 for s in sums), sums
+    finally:
+        plan.close()

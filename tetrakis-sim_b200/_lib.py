@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "tk_graph_plan_create", "tk_lattice_plan_create", "tk_lattice_plan_create_ex",
     "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
-    "tk_plan_run", "tk_plan_launch_count", "tk_plan_destroy",
+    "tk_plan_run", "tk_plan_set_probes", "tk_plan_read_probes", "tk_plan_launch_count", "tk_plan_destroy",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
     "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
     "tk_lattice_ipc_export", "tk_ipc_open", "tk_ipc_close", "tk_lattice_peer_attach",
@@ -104,6 +104,8 @@ def lib():
     L.tk_plan_set_state.argtypes = [P, P, P]
     L.tk_plan_get_state.argtypes = [P, P, P]
     L.tk_plan_run.argtypes = [P, POINTER(RunArgs)]
+    L.tk_plan_set_probes.argtypes = [P, c_int64, P, c_int64]
+    L.tk_plan_read_probes.argtypes = [P, P, POINTER(c_int64)]
     L.tk_plan_launch_count.argtypes = [P, POINTER(c_int64)]
     L.tk_plan_destroy.argtypes = [P]
     L.tk_lattice_halo_ptrs.argtypes = [P, c_int32, POINTER(P), POINTER(P), POINTER(P), POINTER(P),
@@ -308,6 +310,18 @@ class Plan:
         return {"probes": pout, "history": hout, "energy": eout,
                 "elapsed_ms": ms.value if timed else None,
                 "step_kernel_ms": kms.value if timed else None}
+
+    def set_probes(self, probes, rows: int):
+        """Record these nodes at the next ``rows`` finalise calls of a phase-driven run."""
+        pidx = _arr(probes, np.int64)
+        self._n_probes = len(pidx)
+        check(lib().tk_plan_set_probes(self._h, len(pidx), _p(pidx), int(rows)))
+
+    def read_probes(self, max_rows: int):
+        out = np.empty((max_rows, max(getattr(self, "_n_probes", 0), 1)), dtype=np.float64)
+        n = c_int64(0)
+        check(lib().tk_plan_read_probes(self._h, _p(out), ctypes.byref(n)))
+        return out[: n.value, : getattr(self, "_n_probes", 0)]
 
     # -- slab phases (multi-GPU) --------------------------------------------------------------
     def halo_ptrs(self, next_state: bool = False):

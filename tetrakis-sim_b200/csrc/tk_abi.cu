@@ -1344,6 +1344,26 @@ int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchu
     return TK_OK;
 }
 
+int tk_plan_set_probes(tk_plan *p, int64_t n_probes, const int64_t *probe_index, int64_t rows)
+{
+    TK_REQUIRE(p, "plan is NULL");
+    TK_REQUIRE(n_probes >= 0 && rows >= 0 && (n_probes == 0 || probe_index), "bad probe arguments");
+    TK_CUDA(cudaSetDevice(p->device));
+    return set_probes(p, n_probes, probe_index, rows);
+}
+
+int tk_plan_read_probes(tk_plan *p, double *out, int64_t *rows_recorded)
+{
+    TK_REQUIRE(p && rows_recorded, "NULL argument");
+    TK_CUDA(cudaSetDevice(p->device));
+    TK_CUDA(cudaStreamSynchronize(p->stream));
+    *rows_recorded = p->probe_row;
+    if (out && p->n_probes > 0 && p->probe_row > 0)
+        TK_CUDA(cudaMemcpy(out, p->probe_series, (size_t)p->probe_row * p->n_probes * sizeof(double),
+                           cudaMemcpyDeviceToHost));
+    return TK_OK;
+}
+
 int tk_plan_launch_count(const tk_plan *p, int64_t *launches)
 {
     TK_REQUIRE(p && launches, "NULL argument");

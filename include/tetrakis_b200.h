@@ -183,6 +183,9 @@ int tk_ipc_close(int device, void *dev_ptr);
  * peer_layers: number of layers the neighbour owns.  Pass NULL pointers to detach that side. */
 int tk_lattice_peer_attach(tk_plan *plan, int32_t side, void *peer_buf0, void *peer_buf1,
                            int32_t peer_layers);
+/* in_kernel = 1 (default): the step kernel pushes the boundary planes itself (fused).  0: it does not;
+ * the caller moves them with tk_lattice_push_halos after the step (copy engines, off the SMs). */
+int tk_lattice_set_push_mode(tk_plan *plan, int32_t in_kernel);
 /* Copy the boundary planes of the CURRENT state into the attached neighbours' halos (initial fill). */
 int tk_lattice_push_halos(tk_plan *plan, void *cuda_stream);
 /* Stream-ordered: write `value` into both attached neighbours' arrival flags / wait until both of

@@ -50,14 +50,14 @@ def _worker(rank, world, port, out, transport):
         if rank == 0:
             np.save(os.path.join(out, "maxdeg.npy"), np.array([md]))
         dist.barrier()
-        if transport == "p2p":
+        if transport.startswith("p2p"):
             backend.detach_peers()
         backend.plan.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["nccl", "p2p", "p2p-split"])
+@pytest.mark.parametrize("transport", ["nccl", "p2p", "p2p-split", "p2p-copy"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_multi_gpu_slab_run_matches_the_oracle(world, transport, tmp_path):
     import torch

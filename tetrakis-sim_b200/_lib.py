@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
     "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
     "tk_lattice_ipc_export", "tk_ipc_open", "tk_ipc_close", "tk_lattice_peer_attach",
-    "tk_lattice_push_halos", "tk_lattice_signal", "tk_lattice_wait", "tk_lattice_state_ptrs", "tk_dft_abs", "tk_ensemble_run",
+    "tk_lattice_set_push_mode", "tk_lattice_push_halos", "tk_lattice_signal", "tk_lattice_wait", "tk_lattice_state_ptrs", "tk_dft_abs", "tk_ensemble_run",
 )  # fmt: skip
 
 
@@ -118,6 +118,7 @@ def lib():
     L.tk_ipc_open.argtypes = [c_int, P, POINTER(P)]
     L.tk_ipc_close.argtypes = [c_int, P]
     L.tk_lattice_peer_attach.argtypes = [P, c_int32, P, P, c_int32]
+    L.tk_lattice_set_push_mode.argtypes = [P, c_int32]
     L.tk_lattice_push_halos.argtypes = [P, P]
     L.tk_lattice_signal.argtypes = [P, ctypes.c_uint64, P]
     L.tk_lattice_wait.argtypes = [P, ctypes.c_uint64, P]
@@ -355,6 +356,9 @@ class Plan:
     def peer_attach(self, side: int, buf0, buf1, peer_layers: int):
         check(lib().tk_lattice_peer_attach(self._h, int(side), c_void_p(buf0), c_void_p(buf1),
                                            int(peer_layers)))
+
+    def set_push_mode(self, in_kernel: bool):
+        check(lib().tk_lattice_set_push_mode(self._h, 1 if in_kernel else 0))
 
     def push_halos(self, cuda_stream: int = 0):
         check(lib().tk_lattice_push_halos(self._h, c_void_p(cuda_stream)))

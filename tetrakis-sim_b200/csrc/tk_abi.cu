@@ -128,6 +128,7 @@ struct tk_plan {
     double *peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [side][buffer]
     int peer_layers[2] = {0, 0};
     unsigned long long *flags = nullptr;     // this rank's arrival flags: [0] from below, [16] from above
+    bool push_in_kernel = true;              // step kernel stores boundary planes into the peers' halos
     int minb = 1;                            // register path: min resident CTAs per SM asked of ptxas
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
@@ -200,8 +201,9 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
     if (K3D && MODE != 1) {
         const long long plane = (long long)p->lat.S * p->lat.S * 4;
         const int nb = p->cur ^ 1;  // every rank swaps in lockstep, so buffer parities agree
-        p->lat.peer_lo = p->peer_buf[0][nb] ? reinterpret_cast<double *>(pptr(p, 0, nb, (p->peer_layers[0] + 1) * plane)) : nullptr;
-        p->lat.peer_hi = p->peer_buf[1][nb] ? p->peer_buf[1][nb] : nullptr;
+        p->lat.peer_lo = (p->push_in_kernel && p->peer_buf[0][nb])
+                             ? reinterpret_cast<double *>(pptr(p, 0, nb, (p->peer_layers[0] + 1) * plane)) : nullptr;
+        p->lat.peer_hi = (p->push_in_kernel && p->peer_buf[1][nb]) ? p->peer_buf[1][nb] : nullptr;
     }
     if (is_f32(p)) {
         if (CPL > 2 || MODE == 2)
@@ -1269,6 +1271,13 @@ int tk_lattice_peer_attach(tk_plan *p, int32_t side, void *b0, void *b1, int32_t
     p->peer_buf[side][0] = (double *)b0;
     p->peer_buf[side][1] = (double *)b1;
     p->peer_layers[side] = peer_layers;
+    return TK_OK;
+}
+
+int tk_lattice_set_push_mode(tk_plan *p, int32_t in_kernel)
+{
+    TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    p->push_in_kernel = in_kernel != 0;
     return TK_OK;
 }
 

@@ -111,8 +111,13 @@ class SlabRunner:
         self._push_count = 0
         self.interior_first = os.environ.get("TK_SLAB_ORDER", "boundary_first") == "interior_first"
         self.split = os.environ.get("TK_SLAB_SPLIT", "0") == "1"
+        self.copy_push = False
+        if self.transport == "p2p-copy":  # peer memory + flags, planes moved by copy engines after the step
+            self.transport, self.copy_push = "p2p", True
         if self.transport == "p2p":
             backend.attach_peers(dist, rank, world, spec)
+            backend.set_push_mode(not self.copy_push)
+        self._ev_copy = None
 
     # -- index helpers --------------------------------------------------------------------------
     def owns(self, global_index: int) -> bool:
@@ -232,6 +237,8 @@ class SlabRunner:
         ranks run the same kernel on the same amount of data, so the wait for the neighbours' flag at
         the top of the next step is a few microseconds; nothing is split, nothing needs overlapping.
         TK_SLAB_SPLIT=1 keeps the boundary-first / interior-concurrent schedule (needed for NCCL)."""
+        if self.copy_push:
+            return self._step_p2p_copy()
         if not self.split:
             b = self.backend
             st = self.main_stream.cuda_stream
@@ -263,6 +270,26 @@ class SlabRunner:
         b.step_end()
         self._ev_end = torch.cuda.Event()
         self._ev_end.record(main)
+
+    def _step_p2p_copy(self):
+        """Peer memory + flags, but the planes travel by cudaMemcpyAsync on a side stream (copy engines)
+        while the finalise runs: the SMs issue no remote stores."""
+        import torch
+
+        b, main, side = self.backend, self.main_stream, self.comm_stream
+        b.wait(self._push_count, main.cuda_stream)  # the neighbours' planes of u_t have landed
+        if self._ev_copy is not None:
+            main.wait_event(self._ev_copy)  # my own outgoing copies of two steps ago no longer read this buffer
+        b.step_layers(0, self.n_local_layers)
+        ev_k = torch.cuda.Event()
+        ev_k.record(main)
+        b.step_end()  # finalise on the main stream; the new state is now "current"
+        side.wait_event(ev_k)
+        b.push_halos(side.cuda_stream)
+        self._push_count += 1
+        b.signal(self._push_count, side.cuda_stream)
+        self._ev_copy = torch.cuda.Event()
+        self._ev_copy.record(side)
 
     def _post_current_stream(self, next_state: bool):
         if self.world == 1 or self.dist is None:
@@ -439,6 +466,7 @@ def bench_slabs(args) -> int:
     dist.barrier()
     if runner.transport == "p2p":
         backend.detach_peers()
+        backend.set_push_mode(True)
     backend.plan.close()
     dist.barrier()
     dist.destroy_process_group()

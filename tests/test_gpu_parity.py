@@ -399,3 +399,32 @@ def test_full_config3_on_one_gpu_uses_64_bit_indexing():
         assert any(abs(s - 0.25 * (1 + steps)) < 1e-10 for s in sums), sums
     finally:
         plan.close()
+
+
+@pytest.mark.parametrize("size,dim,layers,defect", [
+    (1, 2, 1, "none"), (2, 2, 1, "wedge"), (3, 2, 1, "blackhole"), (1, 3, 1, "none"), (1, 3, 4, "none"),
+    (2, 3, 2, "wedge"), (3, 3, 3, "singularity"), (5, 3, 1, "blackhole"), (33, 2, 1, "singularity"),
+    (65, 2, 1, "blackhole"), (64, 3, 2, "wedge"),
+])
+def test_tiny_and_awkward_lattices_spec_route_equals_graph_route(size, dim, layers, defect):
+    """Degenerate shapes (single cell, single layer 3-D, sizes around the 32/64-cell segment widths):
+    the LatticeSpec route against the bit-exact graph route on LatticeSpec.to_networkx()."""
+    kw = dict(size=size, dim=dim, layers=layers, defect=defect)
+    if defect == "blackhole":
+        kw["radius"] = 1.2
+    if defect == "singularity":
+        kw.update(radius=1.0, mass=30.0, potential=0.7, prune_edges=size % 2 == 1)
+    spec = tk.LatticeSpec(**kw)
+    G = spec.to_networkx()
+    nodes = list(G.nodes)
+    kick = spec.kick_node()
+    other = nodes[-1]
+    init = {kick: 1.0, other: -0.3} if other != kick else {kick: 1.0}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        a = tk.run_wave_sim(G, steps=30, initial_data=init, dt=0.2, damping=0.01)
+        b = tk.run_wave_sim(spec, steps=30, initial_data=init, dt=0.2, damping=0.01, record="all")
+    assert a.metadata["max_degree"] == b.metadata["max_degree"] and a.dt == b.dt
+    idx = np.array([spec.index(n) for n in nodes])
+    assert rel_inf(b.array[:, idx], a.array) < 1e-12
+    assert spec.num_nodes == len(nodes)

@@ -278,13 +278,10 @@ constexpr size_t lat3d_smem()
 template <int WZ, int STAGES, int MINB>
 int launch_lat3d(tk_plan *p, int zl_begin, int zl_end)
 {
-    static bool configured = false;
     auto kern = tk::lat_step3d_kernel<WZ, STAGES, MINB>;
-    if (!configured) {
-        TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)lat3d_smem<WZ, STAGES>()));
-        configured = true;
-    }
+    // per device and cheap: set on every launch rather than caching a per-process flag
+    TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)lat3d_smem<WZ, STAGES>()));
     const int nzg = (zl_end - zl_begin + WZ - 1) / WZ;
     const long long grid = (long long)p->nchunk * p->nsegk * nzg;
     if (grid <= 0) return TK_OK;

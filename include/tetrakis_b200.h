@@ -126,6 +126,9 @@ typedef struct tk_run_args {
                                    A new diagnostic: the reference computes no energy. */
     double *elapsed_ms;         /* host or NULL: device time of the stepping loop (CUDA events) */
     double *step_kernel_ms;     /* host or NULL: summed CUDA-event time of the step kernels alone */
+    int64_t history_stride;     /* 0 or 1: history_out holds every state; k > 1: snapshots of states
+                                   0, k, 2k, ... (floor(steps/k)+1 rows) for runs whose full history
+                                   would not fit anywhere */
 } tk_run_args;
 
 /* physics.py:106-129: `steps` leapfrog updates, synchronous.  The state stays on the device, so

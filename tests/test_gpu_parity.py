@@ -428,3 +428,13 @@ def test_tiny_and_awkward_lattices_spec_route_equals_graph_route(size, dim, laye
     idx = np.array([spec.index(n) for n in nodes])
     assert rel_inf(b.array[:, idx], a.array) < 1e-12
     assert spec.num_nodes == len(nodes)
+
+
+def test_snapshots_every_k_steps_equal_the_full_history():
+    spec = tk.LatticeSpec(size=40, dim=3, layers=5, defect="blackhole", radius=2.5)
+    k = spec.kick_node()
+    full = tk.run_wave_sim(spec, steps=23, initial_data={k: 1.0}, dt=0.05, record="all")
+    snap = tk.run_wave_sim(spec, steps=23, initial_data={k: 1.0}, dt=0.05, record="all", snapshot_every=5)
+    assert snap.array.shape == (5, spec.num_slots)
+    assert np.array_equal(snap.array, full.array[::5])
+    assert np.array_equal(snap.final_state, full.array[-1]) and np.array_equal(snap.probe_series, full.probe_series)

@@ -57,7 +57,7 @@ class RunArgs(ctypes.Structure):
         ("steps", c_int64), ("coeff", c_double), ("damping", c_double),
         ("n_probes", c_int64), ("probe_index", c_void_p), ("probe_out", c_void_p),
         ("history_out", c_void_p), ("energy_out", c_void_p), ("elapsed_ms", c_void_p),
-        ("step_kernel_ms", c_void_p),
+        ("step_kernel_ms", c_void_p), ("history_stride", c_int64),
     ]  # fmt: skip
 
 
@@ -291,7 +291,7 @@ class Plan:
 
     # -- stepping -----------------------------------------------------------------------------
     def run(self, steps, coeff, damping, *, probes=None, history=False, timed=False,
-            probe_out=None, history_out=None, energy=False):  # fmt: skip
+            probe_out=None, history_out=None, energy=False, history_stride=1):  # fmt: skip
         """``steps`` leapfrog updates.  Returns dict(probes, history, energy, elapsed_ms, ...)."""
         steps = int(steps)
         pidx = _arr(probes if probes is not None else [], np.int64)
@@ -301,12 +301,14 @@ class Plan:
         hout = None
         if history:
             hout = (history_out if history_out is not None
-                    else np.empty((steps + 1, self.num_nodes), dtype=np.float64))  # fmt: skip
+                    else np.empty((steps // max(int(history_stride), 1) + 1, self.num_nodes),
+                                  dtype=np.float64))  # fmt: skip
         ms, kms = c_double(0.0), c_double(0.0)
         eout = np.empty(steps, dtype=np.float64) if energy else None
         a = RunArgs(steps, float(coeff), float(damping), len(pidx), _p(pidx), _p(pout), _p(hout),
                     _p(eout), ctypes.cast(ctypes.byref(ms), c_void_p) if timed else None,
-                    ctypes.cast(ctypes.byref(kms), c_void_p) if timed else None)  # fmt: skip
+                    ctypes.cast(ctypes.byref(kms), c_void_p) if timed else None,
+                    max(int(history_stride), 1))  # fmt: skip
         check(lib().tk_plan_run(self._h, ctypes.byref(a)))
         return {"probes": pout, "history": hout, "energy": eout,
                 "elapsed_ms": ms.value if timed else None,

@@ -1081,12 +1081,15 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     long long chunk_rows = 0;
     double *d_hist = nullptr;
     if (a->history_out && p->n > 0) {
-        chunk_rows = std::max<long long>(1, std::min<long long>(a->steps + 1, (long long)(kHistoryChunkBytes / row_bytes)));
+        const long long rows_total = a->steps / (a->history_stride > 1 ? a->history_stride : 1) + 1;
+        chunk_rows = std::max<long long>(1, std::min<long long>(rows_total, (long long)(kHistoryChunkBytes / row_bytes)));
         TK_CUDA(cudaMalloc((void **)&d_hist, (size_t)chunk_rows * row_bytes));
     }
-    long long hist_fill = 0, hist_done = 0;
+    long long hist_fill = 0, hist_done = 0, hist_step = 0;
+    const long long hist_stride = a->history_stride > 1 ? a->history_stride : 1;
     auto record = [&]() -> cudaError_t {
         if (!d_hist) return cudaSuccess;
+        if ((hist_step++ % hist_stride) != 0) return cudaSuccess;
         cudaError_t e = cudaSuccess;
         if (is_f32(p)) {
             tk::f32_to_f64_kernel<<<1024, 256, 0, p->stream>>>(

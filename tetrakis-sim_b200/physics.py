@@ -17,6 +17,9 @@ Extra keyword-only arguments (all optional; the positional signature is the refe
   dtype    "float64" (default; the parity mode) or "float32" for a LatticeSpec: fp32 state, fp64
            row/column sums and Laplacian; relative error vs fp64 about 1e-6 after 100 steps and
            growing ~linearly (tests/test_gpu_fp32.py); not for parity work
+  snapshot_every  (LatticeSpec, record="all") keep only states 0, k, 2k, ... in ``history.array`` --
+           whole-lattice snapshots for runs whose full history would not fit (the probe series is
+           still recorded at every step)
   energy   also return ``history.energy``: the staggered discrete energy between consecutive states,
            ``steps`` values, conserved to rounding when damping == 0 (a new diagnostic; the reference
            computes no energy -- SURVEY.md section 2)
@@ -182,7 +185,7 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
 
 
 def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device, record, probes, energy,
-                 dtype="float64"):
+                 dtype="float64", snapshot_every=1):
     plan = compile_lattice(spec, device=device, dtype=dtype)
     try:
         effective_dt, metadata = _cfl(plan.max_degree, c, dt, steps, damping)
@@ -195,15 +198,20 @@ def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device,
         pnodes = list(probes) if probes is not None else list(kicks)
         pidx = [spec.index(p) for p in pnodes]
         if record == "all":
-            out = plan.run(steps, coeff, damping, probes=pidx, history=True, timed=True, energy=energy)
+            out = plan.run(steps, coeff, damping, probes=pidx, history=True, timed=True, energy=energy,
+                           history_stride=snapshot_every)
         else:
             out = plan.run(steps, coeff, damping, probes=pidx, timed=True, energy=energy)
         series = out["probes"] if pidx else np.empty((steps + 1, 0))
         states = [dict(zip(pnodes, row)) for row in series.tolist()]
         hist = SimulationHistory(states, dt=effective_dt, wave_speed=c, metadata=metadata)
         hist.probe_nodes, hist.probe_series = pnodes, series
-        hist.array = out["history"]  # (steps+1, num_slots) in device layout when record="all"
-        hist.final_state = hist.array[-1] if hist.array is not None else plan.get_state()
+        hist.array = out["history"]  # (steps // snapshot_every + 1, num_slots) in device layout when record="all"
+        hist.snapshot_every = snapshot_every
+        if hist.array is not None and steps % max(snapshot_every, 1) == 0:
+            hist.final_state = hist.array[-1]
+        else:
+            hist.final_state = plan.get_state()
         hist.elapsed_ms = out["elapsed_ms"]
         hist.energy = None if out["energy"] is None else out["energy"] * (c * c)
         hist.metadata["launches"] = plan.launches
@@ -226,6 +234,7 @@ def run_wave_sim(
     probes: list | None = None,
     energy: bool = False,
     dtype: str = "float64",
+    snapshot_every: int = 1,
 ) -> SimulationHistory:
     """Simulate the discrete wave equation on ``G`` (reference physics.py:41-131).
 
@@ -239,7 +248,7 @@ def run_wave_sim(
         raise ValueError("path must be 'auto', 'graph' or 'structured'")
     if isinstance(G, LatticeSpec):
         return _run_lattice(G, steps, initial_data, c, dt, damping, device, record or "probes", probes, energy,
-                            dtype)
+                            dtype, max(int(snapshot_every), 1))
     if dtype != "float64":
         raise ValueError("dtype='float32' is available for LatticeSpec input only")
     return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes, energy)

@@ -224,3 +224,22 @@ def test_install_patches_the_real_reference_when_it_is_importable():
         sys.path.remove("/root/reference")
         for m in [k for k in sys.modules if k == "tetrakis_sim" or k.startswith("tetrakis_sim.")]:
             del sys.modules[m]
+
+
+def test_row_reordering_is_a_permutation_and_cuts_padding():
+    from tetrakis_sim_b200.compiler import ell_padding_waste, reorder_rows
+
+    rng = np.random.default_rng(1)
+    G = nx.barabasi_albert_graph(3000, 3, seed=2)  # hubs: very uneven degrees
+    nodes, index, rowptr, colidx, degree, inv_mass, potential = graph_arrays(G)
+    assert ell_padding_waste(rowptr) > 0.25
+    for method in ("auto", "degree", "rcm"):
+        perm = reorder_rows(rowptr, colidx, method)
+        assert sorted(perm.tolist()) == list(range(3000))
+    perm = reorder_rows(rowptr, colidx, "degree")
+    rp = np.zeros(3001, dtype=np.int64)
+    np.cumsum(np.diff(rowptr)[perm], out=rp[1:])
+    assert ell_padding_waste(rp) < 0.6 * ell_padding_waste(rowptr)
+    assert reorder_rows(graph_arrays(nx.cycle_graph(100))[2], None, "auto") is None
+    with pytest.raises(ValueError):
+        reorder_rows(rowptr, colidx, "bogus")

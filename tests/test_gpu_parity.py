@@ -438,3 +438,20 @@ def test_snapshots_every_k_steps_equal_the_full_history():
     assert snap.array.shape == (5, spec.num_slots)
     assert np.array_equal(snap.array, full.array[::5])
     assert np.array_equal(snap.final_state, full.array[-1]) and np.array_equal(snap.probe_series, full.probe_series)
+
+
+@pytest.mark.parametrize("reorder", ["none", "degree", "rcm", "auto"])
+def test_row_reordering_keeps_the_graph_kernel_bit_exact(reorder):
+    """Device row order (padding / locality optimisation) must not change a single bit."""
+    g = load_golden("random_graph_multi_kick")
+    G, labels = graph_from_golden(g)
+    G.add_edge(5, 5)
+    h = tk.run_wave_sim(G, steps=g["steps"], initial_data=_initial_data(g, labels), c=g["c"], dt=g["dt"],
+                        damping=g["damping"], reorder=reorder)
+    assert np.array_equal(h.array[g["snap_steps"]], g["states"])
+    import networkx as nx
+
+    B = nx.barabasi_albert_graph(4000, 3, seed=5)
+    a = tk.run_wave_sim(B, steps=40, initial_data={0: 1.0, 17: -0.5}, dt=0.05, reorder="none")
+    b = tk.run_wave_sim(B, steps=40, initial_data={0: 1.0, 17: -0.5}, dt=0.05, reorder=reorder, energy=True)
+    assert np.array_equal(a.array, b.array)

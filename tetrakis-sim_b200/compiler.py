@@ -61,11 +61,62 @@ def graph_arrays(G):
     return nodes, index, rowptr, colidx, degree, inv_mass, potential
 
 
-def compile_graph(G, device: int = 0) -> CompiledGraph:
+def ell_padding_waste(rowptr) -> float:
+    """Fraction of sliced-ELL entries (32-row slices, each padded to its own width) that are padding."""
+    deg = np.diff(rowptr)
+    n = len(deg)
+    if n == 0 or deg.sum() == 0:
+        return 0.0
+    pad = np.zeros(((n + 31) // 32) * 32, dtype=np.int64)
+    pad[:n] = deg
+    stored = int((pad.reshape(-1, 32).max(axis=1) * 32).sum())
+    return 1.0 - float(deg.sum()) / stored
+
+
+def reorder_rows(rowptr, colidx, method: str):
+    """Row permutation for the device layout.  ``perm[k]`` = original row stored at device row k.
+
+    * "degree": stable sort by descending degree -- rows of similar length share a slice, which removes
+      the sliced-ELL padding on graphs with hubs;
+    * "rcm": reverse Cuthill-McKee (scipy) -- neighbours get nearby indices, so the u gathers of a warp
+      touch fewer cache lines on large sparse graphs;
+    * "auto": "degree" when more than a quarter of the ELL entries would be padding, else identity.
+    The neighbour ORDER inside every row is untouched, so results stay bit-identical to the reference."""
+    n = len(rowptr) - 1
+    if method in (None, "none") or n == 0:
+        return None
+    if method == "auto":
+        method = "degree" if ell_padding_waste(rowptr) > 0.25 else "none"
+        if method == "none":
+            return None
+    if method == "degree":
+        return np.argsort(-np.diff(rowptr), kind="stable")
+    if method == "rcm":
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+        A = sp.csr_matrix((np.ones(len(colidx), dtype=np.int8), colidx, rowptr), shape=(n, n))
+        return np.asarray(reverse_cuthill_mckee(A, symmetric_mode=True), dtype=np.int64)
+    raise ValueError("reorder must be 'auto', 'none', 'degree' or 'rcm'")
+
+
+def compile_graph(G, device: int = 0, reorder: str = "auto") -> CompiledGraph:
     nodes, index, rowptr, colidx, degree, inv_mass, potential = graph_arrays(G)
-    plan = Plan.graph(rowptr, colidx, degree, inv_mass, potential, device=device)
     max_degree = int(degree.max()) if len(nodes) else 0
-    return CompiledGraph(plan, nodes, index, max_degree)
+    perm = reorder_rows(rowptr, colidx, reorder)
+    if perm is None:
+        plan = Plan.graph(rowptr, colidx, degree, inv_mass, potential, device=device)
+        return CompiledGraph(plan, nodes, index, max_degree)
+    inv = np.empty(len(perm), dtype=np.int64)
+    inv[perm] = np.arange(len(perm))
+    deg_rows = np.diff(rowptr)[perm]
+    rowptr_p = np.zeros(len(perm) + 1, dtype=np.int64)
+    np.cumsum(deg_rows, out=rowptr_p[1:])
+    # gather each permuted row's neighbour list (original order), renumbered
+    take = np.concatenate([np.arange(rowptr[r], rowptr[r + 1]) for r in perm]) if len(colidx) else np.zeros(0, np.int64)
+    colidx_p = inv[colidx[take]].astype(np.int32)
+    plan = Plan.graph(rowptr_p, colidx_p, degree[perm], inv_mass[perm], potential[perm], device=device)
+    return CompiledGraph(plan, nodes, index, max_degree, state_index=inv)
 
 
 def compile_lattice(spec: LatticeSpec, device: int = 0, z_begin: int = 0, z_end: int | None = None,

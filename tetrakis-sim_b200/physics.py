@@ -11,6 +11,8 @@ Extra keyword-only arguments (all optional; the positional signature is the refe
   path     "auto" | "graph" | "structured".  "graph" is the sliced-ELL kernel that reproduces the
            reference bit for bit on any networkx graph; "structured" the clique-sum kernel
            (always used for a LatticeSpec).  "auto" = graph for networkx input.
+  reorder  graph path only: device row order, "auto" (default) | "none" | "degree" | "rcm"; never
+           changes results (the neighbour order inside a row is kept)
   record   "all" (default for graphs: every state, as the reference returns) or "probes"
            (default for a LatticeSpec: only the probe nodes' time series and the final state).
   probes   nodes to record when record="probes" (default: the kicked nodes)
@@ -130,12 +132,12 @@ def _cfl(max_degree: int, c: float, dt: float, steps: int, damping: float):
     return effective_dt, metadata
 
 
-def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes, energy):
+def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes, energy, reorder="auto"):
     comp: CompiledGraph
     if path == "structured":
         comp = structured_from_graph(G, device=device)
     else:
-        comp = compile_graph(G, device=device)
+        comp = compile_graph(G, device=device, reorder=reorder)
     try:
         nodes, index = comp.nodes, comp.index
         effective_dt, metadata = _cfl(comp.max_degree, c, dt, steps, damping)
@@ -235,6 +237,7 @@ def run_wave_sim(
     energy: bool = False,
     dtype: str = "float64",
     snapshot_every: int = 1,
+    reorder: str = "auto",
 ) -> SimulationHistory:
     """Simulate the discrete wave equation on ``G`` (reference physics.py:41-131).
 
@@ -251,7 +254,8 @@ def run_wave_sim(
                             dtype, max(int(snapshot_every), 1))
     if dtype != "float64":
         raise ValueError("dtype='float32' is available for LatticeSpec input only")
-    return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes, energy)
+    return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes, energy,
+                      reorder)
 
 
 def run_fft(

@@ -243,7 +243,7 @@ def gpu_single(args):
     torch.cuda.synchronize()
     l0 = plan.launches
     with clk:
-        out = plan.run(args.steps, coeff, 0.0, probes=kidx, timed=True)
+        out = plan.run(args.steps, coeff, 0.0, probes=kidx, timed=True, kernel_timing=True)
         torch.cuda.synchronize()
     launches = plan.launches - l0
     ms = out["elapsed_ms"]

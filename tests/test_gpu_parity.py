@@ -455,3 +455,37 @@ def test_row_reordering_keeps_the_graph_kernel_bit_exact(reorder):
     a = tk.run_wave_sim(B, steps=40, initial_data={0: 1.0, 17: -0.5}, dt=0.05, reorder="none")
     b = tk.run_wave_sim(B, steps=40, initial_data={0: 1.0, 17: -0.5}, dt=0.05, reorder=reorder, energy=True)
     assert np.array_equal(a.array, b.array)
+
+
+@pytest.mark.parametrize("steps", [8, 9, 31])
+def test_cuda_graph_replay_equals_direct_launches(steps, monkeypatch):
+    """Launch-bound runs are replayed from a captured CUDA graph (two steps per graph, output rows through
+    device counters); results must be identical to direct launches -- both kernels, probes, history, energy,
+    odd step counts."""
+    import networkx as nx
+
+    spec = tk.LatticeSpec(size=50, dim=3, layers=6, defect="singularity", radius=1.5, mass=40.0, potential=2.0)
+    k = spec.kick_node()
+    G = nx.barabasi_albert_graph(500, 3, seed=1)
+
+    def runs():
+        a = tk.run_wave_sim(spec, steps=steps, initial_data={k: 1.0}, dt=0.05, damping=0.01, record="all",
+                            probes=[k, (0, 0, 0, "A")], energy=True)
+        b = tk.run_wave_sim(spec, steps=steps, initial_data={k: 1.0}, dt=0.05, probes=[k])
+        c = tk.run_wave_sim(G, steps=steps, initial_data={3: 1.0}, dt=0.1, energy=True)
+        d = tk.run_wave_sim(G, steps=steps, initial_data={3: 1.0}, dt=0.1, record="probes", probes=[3, 77])
+        e = tk.run_wave_sim(spec, steps=steps, initial_data={k: 1.0}, dt=0.05, dtype="float32", record="all")
+        return a, b, c, d, e
+
+    monkeypatch.setenv("TK_CUDA_GRAPH", "1")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        g = runs()
+        monkeypatch.setenv("TK_CUDA_GRAPH", "0")
+        h = runs()
+    for x, y in zip(g, h):
+        for f in ("array", "probe_series", "final_state", "energy"):
+            u, v = getattr(x, f), getattr(y, f)
+            assert (u is None) == (v is None)
+            if u is not None:
+                assert np.array_equal(u, v), f

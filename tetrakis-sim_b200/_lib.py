@@ -291,8 +291,13 @@ class Plan:
 
     # -- stepping -----------------------------------------------------------------------------
     def run(self, steps, coeff, damping, *, probes=None, history=False, timed=False,
-            probe_out=None, history_out=None, energy=False, history_stride=1):  # fmt: skip
-        """``steps`` leapfrog updates.  Returns dict(probes, history, energy, elapsed_ms, ...)."""
+            probe_out=None, history_out=None, energy=False, history_stride=1,
+            kernel_timing=False):  # fmt: skip
+        """``steps`` leapfrog updates.  Returns dict(probes, history, energy, elapsed_ms, ...).
+
+        ``timed``: CUDA-event time of the whole stepping loop.  ``kernel_timing``: additionally the summed
+        event time of the step kernels alone (bench.py's roofline); it forces direct launches, whereas
+        launch-bound runs are otherwise replayed from a captured CUDA graph."""
         steps = int(steps)
         pidx = _arr(probes if probes is not None else [], np.int64)
         pout = None
@@ -307,12 +312,12 @@ class Plan:
         eout = np.empty(steps, dtype=np.float64) if energy else None
         a = RunArgs(steps, float(coeff), float(damping), len(pidx), _p(pidx), _p(pout), _p(hout),
                     _p(eout), ctypes.cast(ctypes.byref(ms), c_void_p) if timed else None,
-                    ctypes.cast(ctypes.byref(kms), c_void_p) if timed else None,
+                    ctypes.cast(ctypes.byref(kms), c_void_p) if kernel_timing else None,
                     max(int(history_stride), 1))  # fmt: skip
         check(lib().tk_plan_run(self._h, ctypes.byref(a)))
         return {"probes": pout, "history": hout, "energy": eout,
                 "elapsed_ms": ms.value if timed else None,
-                "step_kernel_ms": kms.value if timed else None}
+                "step_kernel_ms": kms.value if kernel_timing else None}
 
     def set_probes(self, probes, rows: int):
         """Record these nodes at the next ``rows`` finalise calls of a phase-driven run."""

@@ -57,8 +57,10 @@ graph_step_kernel(long long n, const long long *__restrict__ slice_off,
 
 // energy_out = 1/2 * sum(pen[0..n)) in a fixed order
 __global__ void __launch_bounds__(256)
-energy_reduce_kernel(const double *__restrict__ pen, long long n, double *__restrict__ energy_out)
+energy_reduce_kernel(const double *__restrict__ pen, long long n, double *__restrict__ energy_out,
+                     const long long *__restrict__ ctr)
 {
+    if (ctr != nullptr) energy_out += ctr[2];  // graph replay: row from the device counter
     __shared__ double red[256];
     double a = 0.0;
     for (long long i = threadIdx.x; i < n; i += 256) a += pen[i];

@@ -679,8 +679,15 @@ lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, int nrowblk,
                     double *__restrict__ rowinfo, double *__restrict__ colinfo,
                     const void *__restrict__ state, int state_is_f32,
                     const long long *__restrict__ probe_idx, int n_probes, double *__restrict__ probe_row,
-                    const double *__restrict__ pen, long long n_pen, double *__restrict__ energy_out)
+                    const double *__restrict__ pen, long long n_pen, double *__restrict__ energy_out,
+                    const long long *__restrict__ ctr)
 {
+    // ctr != null (CUDA-graph replay): probe_row / energy_out are the BASES of the series and the row
+    // to write comes from device counters (ctr[0] probes, ctr[2] energy), advanced by advance_kernel
+    if (ctr != nullptr) {
+        probe_row += (size_t)ctr[0] * n_probes;
+        if (energy_out != nullptr) energy_out += ctr[2];
+    }
     if (blockIdx.x == 0)
         for (int t = threadIdx.x; t < n_probes; t += blockDim.x)
             probe_row[t] = state_is_f32 ? (double)static_cast<const float *>(state)[probe_idx[t]]
@@ -818,10 +825,26 @@ __global__ void f64_to_f32_kernel(const double *__restrict__ src, float *__restr
 }
 
 __global__ void gather_kernel(const double *__restrict__ src, const long long *__restrict__ idx,
-                              double *__restrict__ out, int n)
+                              double *__restrict__ out, int n, const long long *__restrict__ ctr)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ctr != nullptr) out += (size_t)ctr[0] * n;  // graph replay: row from the device counter
     if (i < n) out[i] = src[idx[i]];
+}
+
+// One state row into the history staging buffer at the row given by a device counter (graph replay).
+__global__ void history_row_kernel(const void *__restrict__ src, int src_is_f32, double *__restrict__ hist,
+                                   long long n, const long long *__restrict__ ctr)
+{
+    double *dst = hist + (size_t)ctr[1] * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src_is_f32 ? (double)static_cast<const float *>(src)[i] : static_cast<const double *>(src)[i];
+}
+
+// End of a replayed step: advance the row counters (probes, history, energy).
+__global__ void advance_kernel(long long *ctr)
+{
+    if (threadIdx.x < 3) ctr[threadIdx.x] += 1;
 }
 
 }  // namespace tk

@@ -129,6 +129,9 @@ struct tk_plan {
     int peer_layers[2] = {0, 0};
     unsigned long long *flags = nullptr;     // this rank's arrival flags: [0] from below, [16] from above
     bool push_in_kernel = true;              // step kernel stores boundary planes into the peers' halos
+    // CUDA-graph replay of the stepping loop: output rows come from device counters
+    long long *ctr_dev = nullptr;            // [0] probe row, [1] history row, [2] energy row
+    bool ctr_mode = false;
     int minb = 1;                            // register path: min resident CTAs per SM asked of ptxas
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
@@ -363,12 +366,15 @@ int lat_finalise(tk_plan *p, const double *state, double *probe_row)
     const int nrowblk = (int)((nline + 7) / 8);
     const int ncolblk = (int)((nline * 4 + 31) / 32);
     double *eout = nullptr;
-    if (p->energy_on && p->pen_used > 0 && p->energy_row < p->energy_cap)
+    if (p->ctr_mode) {
+        if (p->energy_on && p->pen_used > 0) eout = p->energy_series;  // base; the row comes from ctr[2]
+    } else if (p->energy_on && p->pen_used > 0 && p->energy_row < p->energy_cap) {
         eout = p->energy_series + p->energy_row++;
+    }
     tk::lat_finalise_kernel<<<(unsigned)(nrowblk + ncolblk + (eout ? 1 : 0)), 256, 0, p->stream>>>(
         p->lat.S, p->lat.Lloc, p->nsegk, p->nchunk, nrowblk, p->prow, p->pcol, p->rowinfo, p->colinfo,
         state, is_f32(p) ? 1 : 0, p->probe_idx, probe_row ? p->n_probes : 0, probe_row, p->pen, p->pen_used,
-        eout);
+        eout, p->ctr_mode ? p->ctr_dev : nullptr);
     p->pen_used = 0;
     p->launches++;
     TK_CUDA(cudaGetLastError());
@@ -404,6 +410,7 @@ int set_energy(tk_plan *p, bool on, long long steps)
 
 double *next_probe_row(tk_plan *p)
 {
+    if (p->ctr_mode) return p->n_probes > 0 ? p->probe_series : nullptr;  // base; row from ctr[0]
     if (p->n_probes == 0 || p->probe_row >= p->probe_rows_cap) return nullptr;
     return p->probe_series + (size_t)(p->probe_row++) * p->n_probes;
 }
@@ -434,11 +441,14 @@ int graph_step(tk_plan *p, double coeff, double damping)
     const unsigned grid = (unsigned)((p->n + 255) / 256);
     if (grid) {
         const double inv_coeff = coeff > 0.0 ? 1.0 / coeff : 0.0;
-        if (p->energy_on && p->energy_row < p->energy_cap) {
+        if (p->energy_on && (p->ctr_mode || p->energy_row < p->energy_cap)) {
             tk::graph_step_kernel<true><<<grid, 256, 0, p->stream>>>(
                 p->n, p->slice_off, p->ell_idx, p->deg, p->inv_mass, p->potential, p->buf[p->cur],
                 p->buf[p->cur ^ 1], coeff, damping, p->pen, inv_coeff);
-            tk::energy_reduce_kernel<<<1, 256, 0, p->stream>>>(p->pen, grid, p->energy_series + p->energy_row++);
+            if (p->ctr_mode)
+                tk::energy_reduce_kernel<<<1, 256, 0, p->stream>>>(p->pen, grid, p->energy_series, p->ctr_dev);
+            else
+                tk::energy_reduce_kernel<<<1, 256, 0, p->stream>>>(p->pen, grid, p->energy_series + p->energy_row++, nullptr);
             p->launches += 2;
         } else {
             tk::graph_step_kernel<false><<<grid, 256, 0, p->stream>>>(
@@ -450,8 +460,8 @@ int graph_step(tk_plan *p, double coeff, double damping)
     }
     p->cur ^= 1;
     if (double *row = next_probe_row(p)) {
-        tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(p->buf[p->cur], p->probe_idx,
-                                                                           row, p->n_probes);
+        tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(
+            p->buf[p->cur], p->probe_idx, row, p->n_probes, p->ctr_mode ? p->ctr_dev : nullptr);
         p->launches++;
         TK_CUDA(cudaGetLastError());
     }
@@ -1140,12 +1150,87 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     }
     if (p->kind == kGraph) {
         if (double *row = next_probe_row(p)) {
-            tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(p->buf[p->cur], p->probe_idx, row, p->n_probes);
+            tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(p->buf[p->cur], p->probe_idx, row, p->n_probes, nullptr);
             p->launches++;
         }
         TK_RUN_CUDA(record());
         if (ev0) TK_RUN_CUDA(cudaEventRecord(ev0, p->stream));
-        for (int64_t s = 0; s < a->steps; ++s) {
+    } else {
+        TK_RUN_TRY(tk_lattice_step_begin(p, a->coeff, a->damping));
+        TK_RUN_CUDA(record());
+        if (ev0) TK_RUN_CUDA(cudaEventRecord(ev0, p->stream));
+    }
+
+    // ---- launch-bound problems: capture two steps (the buffers alternate) into a CUDA graph and replay
+    // it; output rows (probes / history / energy) are addressed through device counters so the captured
+    // launches are identical every time.  Large lattices gain nothing (their kernels take ~1 ms) and the
+    // per-kernel event timing cannot be captured, so both keep the direct launches below.
+    int64_t steps_left = a->steps;
+    const bool hist_in_one_chunk = !d_hist || (hist_stride == 1 && chunk_rows >= a->steps + 1);
+    const bool use_graph = a->steps >= 8 && !a->step_kernel_ms && hist_in_one_chunk && p->n <= (1LL << 24) &&
+                           env_int("TK_CUDA_GRAPH", 1) != 0;
+    if (use_graph) {
+        if (!p->ctr_dev) {
+            TK_RUN_CUDA(cudaMalloc((void **)&p->ctr_dev, 4 * sizeof(long long)));
+        }
+        const long long ctr0[4] = {p->probe_row, hist_fill, p->energy_row, 0};
+        TK_RUN_CUDA(cudaMemcpyAsync(p->ctr_dev, ctr0, sizeof(ctr0), cudaMemcpyHostToDevice, p->stream));
+        TK_RUN_CUDA(cudaStreamSynchronize(p->stream));  // ctr0 is a stack array
+        auto one_step = [&]() -> int {
+            int r = p->kind == kGraph ? graph_step(p, a->coeff, a->damping)
+                                      : tk_lattice_step_layers(p, 0, p->lat.Lloc);
+            if (r == TK_OK && p->kind != kGraph) r = tk_lattice_step_end(p);
+            if (r) return r;
+            if (d_hist) {
+                tk::history_row_kernel<<<256, 256, 0, p->stream>>>(bptr(p, p->cur, p->state_off), is_f32(p) ? 1 : 0,
+                                                                  d_hist, p->n, p->ctr_dev);
+                p->launches++;
+            }
+            tk::advance_kernel<<<1, 32, 0, p->stream>>>(p->ctr_dev);
+            p->launches++;
+            return cudaGetLastError() == cudaSuccess ? TK_OK : fail(TK_ERR_CUDA, "graph-mode launch failed");
+        };
+        p->ctr_mode = true;
+        const long long launches_before = p->launches;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal);
+        int rcap = TK_OK;
+        if (ce == cudaSuccess) {
+            rcap = one_step();
+            if (rcap == TK_OK) rcap = one_step();
+            ce = cudaStreamEndCapture(p->stream, &graph);
+        }
+        if (ce == cudaSuccess && rcap == TK_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
+        const long long per_pair = p->launches - launches_before;
+        if (ce != cudaSuccess || rcap != TK_OK) {
+            p->ctr_mode = false;
+            if (graph) cudaGraphDestroy(graph);
+            if (d_hist) cudaFree(d_hist);
+            if (rcap != TK_OK) return rcap;
+            return fail(TK_ERR_CUDA, "CUDA graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        const int64_t pairs = a->steps / 2;
+        for (int64_t i = 0; i < pairs && ce == cudaSuccess; ++i) ce = cudaGraphLaunch(exec, p->stream);
+        p->launches = launches_before + per_pair * pairs;
+        if (ce == cudaSuccess && (a->steps & 1)) {
+            const int r = one_step();
+            if (r) ce = cudaErrorUnknown;
+        }
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        p->ctr_mode = false;
+        if (ce != cudaSuccess) {
+            if (d_hist) cudaFree(d_hist);
+            return fail(TK_ERR_CUDA, "CUDA graph replay failed: %s", cudaGetErrorString(ce));
+        }
+        p->probe_row += p->n_probes > 0 ? a->steps : 0;
+        p->energy_row += p->energy_on ? a->steps : 0;
+        if (d_hist) hist_fill += a->steps;
+        steps_left = 0;
+    }
+    if (p->kind == kGraph) {
+        for (int64_t s = 0; s < steps_left; ++s) {
             const bool tk_ = (size_t)(2 * s + 1) < kev.size();
             if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s], p->stream));
             TK_RUN_TRY(graph_step(p, a->coeff, a->damping));
@@ -1153,10 +1238,7 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
             TK_RUN_CUDA(record());
         }
     } else {
-        TK_RUN_TRY(tk_lattice_step_begin(p, a->coeff, a->damping));
-        TK_RUN_CUDA(record());
-        if (ev0) TK_RUN_CUDA(cudaEventRecord(ev0, p->stream));
-        for (int64_t s = 0; s < a->steps; ++s) {
+        for (int64_t s = 0; s < steps_left; ++s) {
             const bool tk_ = (size_t)(2 * s + 1) < kev.size();
             if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s], p->stream));
             TK_RUN_TRY(tk_lattice_step_layers(p, 0, p->lat.Lloc));
@@ -1390,6 +1472,7 @@ int tk_plan_destroy(tk_plan *p)
     if (p->probe_series) cudaFree(p->probe_series);
     if (p->pen) cudaFree(p->pen);
     if (p->energy_series) cudaFree(p->energy_series);
+    if (p->ctr_dev) cudaFree(p->ctr_dev);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return TK_OK;

@@ -420,7 +420,7 @@ def bench_slabs(args) -> int:
 
     # roofline of the step kernel on this rank's slab, no communication (rank 0 reports)
     backend.set_state_sparse(*kicks)
-    o = backend.plan.run(min(args.steps, 50), coeff, 0.0, timed=True)
+    o = backend.plan.run(min(args.steps, 50), coeff, 0.0, timed=True, kernel_timing=True)
     kms = o["step_kernel_ms"] / min(args.steps, 50)
     alone_ms = o["elapsed_ms"] / min(args.steps, 50)  # this rank's slab stepped alone: step + finalise
     local_nodes = backend.num_nodes  # slots; the black hole removes < 1 %

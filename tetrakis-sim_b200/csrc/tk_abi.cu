@@ -783,7 +783,9 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
 
     // ---- kernel variant + tiling
     p->cpl = env_int("TK_LAT_CPL", 1);
-    p->wc = env_int("TK_LAT_WC", halo ? 1 : 8);
+    // 2-D: 8 adjacent segments per CTA -- unless the rows are too short to have 8 (idle warps otherwise)
+    const int nseg32 = (int)((S + 31) / 32);
+    p->wc = env_int("TK_LAT_WC", halo ? 1 : (nseg32 >= 8 ? 8 : (nseg32 >= 2 ? 2 : 1)));
     // defaults from the round-1 sweeps on B200 (profiles/r01_sweeps.md): 2-D 3 CTAs/SM + 1-row L2
     // prefetch; 3-D 2 CTAs/SM + 2-row prefetch
     p->minb = env_int("TK_LAT_MINB", p->cpl == 1 ? (halo ? 2 : 3) : 1);
@@ -817,6 +819,18 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
                                               : lat_occupancy(p->cpl, p->wc, p->minb, halo != 0));
         int best = 16;
         double best_eff = -1.0;
+        // Small lattices never fill the machine: a step is then bound by the serial march of one warp
+        // down its rows (~1 us per row out of L2), not by bandwidth, so use the SHORTEST march that still
+        // gives about one CTA per slot (measured: 512^2 went from 20 to ~8 us per step).
+        const long long tiles16 = ((S + 15) / 16) * nct * nzg;
+        if (tiles16 < slots) {
+            const long long per_row_block = std::max<long long>(1, nct * nzg);
+            const long long want_chunks = std::max<long long>(1, slots / per_row_block);
+            long long rc_small = (S + want_chunks - 1) / want_chunks;
+            rc_small = std::max<long long>(4, std::min<long long>(rc_small, 16));
+            best = (int)rc_small;
+            best_eff = 2.0;  // skip the throughput search below
+        }
         // (cap at 128 rows: longer marches measured slower -- cfg4 512^3: 256 rows 226 GNUPS, 64-128
         // rows 244 -- CTAs of neighbouring z-groups drift apart and lose the shared z+-1 lines in L2)
         for (int rc_ = 16; rc_ <= 128 && rc_ <= std::max<long long>(16, S); ++rc_) {

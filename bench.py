@@ -141,7 +141,14 @@ def cpu_run(workload: str, steps: int, warmup: int, budget_s: float):
     from oracle import wave_oracle as wo
 
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     three_d = workload.startswith("cfg3")
 
     def shape(size):
@@ -160,7 +167,7 @@ def cpu_run(workload: str, steps: int, warmup: int, budget_s: float):
     t, n = one(256, 4)  # calibrate seconds per node-update
     per_nu = max(t / (4 * n), 1e-12)
     size = 256
-    for cand in (512, 1024, 2048, 4096):
+    for cand in ((128, 256, 512, 1024) if three_d else (512, 1024, 2048, 4096)):
         S, L = shape(cand)
         if (steps + warmup) * L * cand * cand * 4 * per_nu <= budget_s:
             size = cand

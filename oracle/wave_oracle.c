@@ -116,14 +116,21 @@ int tko_structured_run(int32_t layers, int32_t size, const uint8_t *flags, const
                 }
             for (int q = 0; q < 4; ++q) rowsum[zr * 4 + q] = acc[q];
         }
-#pragma omp parallel for schedule(static)
-        for (int64_t z = 0; z < L; ++z) {
-            double *cs = colsum + z * S * 4;
-            memset(cs, 0, sizeof(double) * (size_t)(S * 4));
-            for (int64_t r = 0; r < S; ++r)
-                for (int64_t cq = 0; cq < S * 4; ++cq) {
-                    int64_t i = (z * S + r) * S * 4 + cq;
-                    if (PART(i)) cs[cq] += u[i];
+        /* column sums: threads over (layer, block of 128 column entries); each walks the rows in order,
+         * so every column's sum has a fixed order whatever the thread count */
+        {
+            const int64_t W = S * 4, nblk = (W + 127) / 128;
+#pragma omp parallel for collapse(2) schedule(static)
+            for (int64_t z = 0; z < L; ++z)
+                for (int64_t blk = 0; blk < nblk; ++blk) {
+                    const int64_t lo = blk * 128, hi = lo + 128 < W ? lo + 128 : W;
+                    double *cs = colsum + z * W;
+                    for (int64_t cq = lo; cq < hi; ++cq) cs[cq] = 0.0;
+                    for (int64_t r = 0; r < S; ++r) {
+                        const int64_t base = (z * S + r) * W;
+                        for (int64_t cq = lo; cq < hi; ++cq)
+                            if (PART(base + cq)) cs[cq] += u[base + cq];
+                    }
                 }
         }
         /* corrections read u_t, so gather them before u is overwritten (uprev <- unew in place) */

@@ -110,6 +110,17 @@ def test_3d_staged_kernel_variants_against_the_oracle(wz, stages, rchunk, case, 
     _variant_case(1, 1, rchunk, case, monkeypatch)
 
 
+@pytest.mark.parametrize("stages,rchunk", [(4, 0), (2, 16), (3, 40), (6, 5), (4, 3), (3, 128)])
+@pytest.mark.parametrize("case", ["2d_hole", "3d_sing", "3d_wedge_odd", "3d_hole_tall"])
+def test_tma_staged_kernel_variants_against_the_oracle(stages, rchunk, case, monkeypatch):
+    """lat_step_bulk_kernel (cp.async.bulk + mbarrier, a private ring per warp): ragged last segments
+    (short bulk copies), row chunks shorter than the ring, defect rows, 2-D and 3-D."""
+    monkeypatch.setenv("TK_LAT3D", "0")
+    monkeypatch.setenv("TK_LAT_BULK", "1")
+    monkeypatch.setenv("TK_LAT_BULK_STAGES", str(stages))
+    _variant_case(1, 1, rchunk, case, monkeypatch)
+
+
 def _variant_case(cpl, wc, rchunk, case, monkeypatch):
     monkeypatch.setenv("TK_LAT_CPL", str(cpl))
     monkeypatch.setenv("TK_LAT_WC", str(wc))

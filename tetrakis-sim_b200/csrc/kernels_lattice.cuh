@@ -330,6 +330,165 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
     }
 }
 
+// TMA variant of lat_step_kernel (fp64, one cell per lane): every warp is its own producer and consumer.
+//
+// Lane 0 issues cp.async.bulk copies (SASS UBLKCP) of the warp's next row segments -- u, u_prev, in 3-D also
+// the z-1 / z+1 segments, plus the row's 64-byte {RowSum, rowcnt} record and its defect-table entry -- into a
+// per-warp ring of STAGES shared-memory stages, each completing on its own mbarrier; all lanes wait on the
+// stage's phase, copy their 32 bytes to registers, and lane 0 re-arms the stage for row r+STAGES.  No CTA-wide
+// barrier (the cp.async version's problem), no registers spent on prefetching, STAGES rows in flight per warp.
+template <int WC, bool K3D, int STAGES, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+lat_step_bulk_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u, double *__restrict__ w,
+                     double *__restrict__ prow, double *__restrict__ pcol, double coeff, double damping,
+                     int zl_begin, int zl_end, int rchunk, int nchunk, int nsegk, int nct, int nzg)
+{
+    constexpr int WZ = 8 / WC;
+    constexpr int NARR = K3D ? 4 : 2;
+    constexpr int STAGE_DOUBLES = NARR * 128 + 16;  // + 8 doubles rowinfo + 16 B table entry (padded to 128 B)
+    extern __shared__ __align__(16) unsigned char tk_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *ring = reinterpret_cast<double *>(tk_smem) + (size_t)warp * STAGES * STAGE_DOUBLES;
+    unsigned long long *bars =
+        reinterpret_cast<unsigned long long *>(tk_smem + (size_t)8 * STAGES * STAGE_DOUBLES * sizeof(double)) + warp * STAGES;
+    int b = blockIdx.x;
+    const int zg = b % nzg;
+    b /= nzg;
+    const int ct = b % nct;
+    const int ch = b / nct;
+    const int zl = zl_begin + zg * WZ + warp / WC;
+    const int segk = ct * WC + warp % WC;
+    if (zl >= zl_end || segk >= nsegk) return;  // per-warp barriers only: a whole warp may leave
+
+    const int S = P.S;
+    const int cw = segk * 32;                   // first cell of the warp's segment
+    const int c0 = cw + lane;
+    const bool valid = c0 < S;
+    const unsigned seg_bytes = (unsigned)min(32, S - cw) * 32u;
+    const size_t plane = (size_t)S * S * 4;
+    const size_t zbase = (size_t)(zl + P.halo) * plane;
+    const unsigned fplain = plain_flags(P, zl);
+    const bool zm_on = K3D && (fplain & 0x100u), zp_on = K3D && (fplain & 0x1000u);
+    const double degbase = 4.0 + (zm_on ? 1.0 : 0.0) + (zp_on ? 1.0 : 0.0);
+    const int tab0 = cw / kTabSeg;
+
+    double CS[4] = {0, 0, 0, 0}, CC[4] = {0, 0, 0, 0}, cacc[4] = {0, 0, 0, 0};
+    if (valid) {
+        ld256_nc(P.colinfo + ((size_t)zl * S + c0) * 8, CS);
+        ld256_nc(P.colinfo + ((size_t)zl * S + c0) * 8 + 4, CC);
+    }
+    const int r_begin = ch * rchunk;
+    const int r_end = min(S, r_begin + rchunk);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        fence_proxy_async();  // make the initialised barriers visible to the async proxy
+    }
+    __syncwarp();
+    const unsigned tx = seg_bytes * (2u + (zm_on ? 1u : 0u) + (zp_on ? 1u : 0u)) + 64u + 16u;
+    auto issue = [&](int r, int s) {  // lane 0
+        double *st = ring + (size_t)s * STAGE_DOUBLES;
+        const size_t off = zbase + ((size_t)r * S + cw) * 4;
+        mbar_expect_tx(&bars[s], tx);
+        bulk_g2s(st, u + off, seg_bytes, &bars[s]);
+        bulk_g2s(st + 128, w + off, seg_bytes, &bars[s]);
+        if (zm_on) bulk_g2s(st + 256, u + off - plane, seg_bytes, &bars[s]);
+        if (zp_on) bulk_g2s(st + 384, u + off + plane, seg_bytes, &bars[s]);
+        bulk_g2s(st + NARR * 128, P.rowinfo + ((size_t)zl * S + r) * 8, 64u, &bars[s]);
+        // the 4-byte table entry travels inside its 16-byte aligned quad (the table is padded at the end)
+        const size_t fi = ((size_t)zl * S + r) * P.ntab + tab0;
+        bulk_g2s(st + NARR * 128 + 8, P.seg_flag + (fi & ~(size_t)3), 16u, &bars[s]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i)
+            if (r_begin + i < r_end) issue(r_begin + i, i);
+    }
+    int s = 0;
+    unsigned parity = 0;
+    for (int r = r_begin; r < r_end; ++r) {
+        const double *st = ring + (size_t)s * STAGE_DOUBLES;
+        mbar_wait(&bars[s], parity);
+        double uq[4], upq[4], zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0}, RS[4], RC[4];
+        {
+            const double2 a = *reinterpret_cast<const double2 *>(st + lane * 4);
+            const double2 bb = *reinterpret_cast<const double2 *>(st + lane * 4 + 2);
+            uq[0] = a.x; uq[1] = a.y; uq[2] = bb.x; uq[3] = bb.y;
+            const double2 c = *reinterpret_cast<const double2 *>(st + 128 + lane * 4);
+            const double2 d = *reinterpret_cast<const double2 *>(st + 128 + lane * 4 + 2);
+            upq[0] = c.x; upq[1] = c.y; upq[2] = d.x; upq[3] = d.y;
+            if (zm_on) {
+                const double2 e = *reinterpret_cast<const double2 *>(st + 256 + lane * 4);
+                const double2 f = *reinterpret_cast<const double2 *>(st + 256 + lane * 4 + 2);
+                zm[0] = e.x; zm[1] = e.y; zm[2] = f.x; zm[3] = f.y;
+            }
+            if (zp_on) {
+                const double2 e = *reinterpret_cast<const double2 *>(st + 384 + lane * 4);
+                const double2 f = *reinterpret_cast<const double2 *>(st + 384 + lane * 4 + 2);
+                zp[0] = e.x; zp[1] = e.y; zp[2] = f.x; zp[3] = f.y;
+            }
+            const double2 r0 = *reinterpret_cast<const double2 *>(st + NARR * 128);
+            const double2 r1 = *reinterpret_cast<const double2 *>(st + NARR * 128 + 2);
+            const double2 r2 = *reinterpret_cast<const double2 *>(st + NARR * 128 + 4);
+            const double2 r3 = *reinterpret_cast<const double2 *>(st + NARR * 128 + 6);
+            RS[0] = r0.x; RS[1] = r0.y; RS[2] = r1.x; RS[3] = r1.y;
+            RC[0] = r2.x; RC[1] = r2.y; RC[2] = r3.x; RC[3] = r3.y;
+        }
+        const size_t fi = ((size_t)zl * S + r) * P.ntab + tab0;
+        const int det_w = reinterpret_cast<const int *>(st + NARR * 128 + 8)[fi & 3];
+        if (!valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { uq[q] = 0.0; upq[q] = 0.0; zm[q] = 0.0; zp[q] = 0.0; }
+        }
+        __syncwarp();  // every lane has taken its values: the stage may be refilled
+        if (lane == 0 && r + STAGES < r_end) {
+            fence_proxy_async();
+            issue(r + STAGES, s);
+        }
+        const int det = valid ? det_w : -1;
+        const bool all_plain = det_w < 0;  // one table entry per 64 cells: warp-uniform
+        const size_t rowoff = zbase + ((size_t)r * S + c0) * 4;
+        double un[4], pun[4];
+        if (all_plain) {
+            const double cell = (uq[0] + uq[1]) + (uq[2] + uq[3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double nb = (cell + RS[q]) + (CS[q] + (zm[q] + zp[q]));
+                const double dg = (RC[q] + degbase) + CC[q];
+                const double lap = nb - dg * uq[q];
+                un[q] = 2.0 * uq[q] - upq[q] + coeff * lap - damping * (uq[q] - upq[q]);
+                pun[q] = valid ? un[q] : 0.0;
+            }
+        } else {
+            unsigned f = fplain;
+            if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + (c0 & (kTabSeg - 1))];
+            if (!valid) f = 0;
+            CellIO io;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                io.uq[q] = uq[q]; io.upq[q] = upq[q]; io.zm[q] = zm[q]; io.zp[q] = zp[q];
+                io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[q]; io.CC[q] = CC[q];
+            }
+            cell_update_detail(P, u, det, c0 & (kTabSeg - 1), (long long)rowoff, f, coeff, damping, 0.0, io);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { un[q] = io.un[q]; pun[q] = io.pun[q]; }
+        }
+        if (valid) {
+            st256_cs(w + rowoff, un);
+            if (K3D) {
+                if (zl == 0 && P.peer_lo) st256(P.peer_lo + (rowoff - zbase), un);
+                if (zl == P.Lloc - 1 && P.peer_hi) st256(P.peer_hi + (rowoff - zbase), un);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cacc[q] += pun[q];
+        warp_sum4_store(pun, lane, prow + (((size_t)zl * S + r) * nsegk + segk) * 4);
+        if (++s == STAGES) { s = 0; parity ^= 1u; }
+    }
+    if (valid) st256(pcol + (((size_t)zl * nchunk + ch) * S + c0) * 4, cacc);
+}
+
 // fp32 state variant of lat_step_kernel (optional mode; 12 B/update).
 //
 // Storage and the update expression are fp32; the Laplacian -- a difference of two sums of up to

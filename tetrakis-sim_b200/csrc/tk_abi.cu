@@ -115,6 +115,7 @@ struct tk_plan {
     tk::LatDev lat{};
     double *rowinfo = nullptr, *colinfo = nullptr, *prow = nullptr, *pcol = nullptr;
     int cpl = 2, wc = 8, rchunk = 64, nchunk = 1, nsegk = 1;
+    int bulk_stages = 0;                     // > 0: fp64 steps use lat_step_bulk_kernel with this many stages
     int wz3d = 0, stages3d = 0, minb3d = 2;  // wz3d > 0: 3-D steps use lat_step3d_kernel<wz3d, stages3d, minb3d>
     int pf_rows = 0;                         // register path: L2 prefetch distance in rows (0 = off)
     // energy series (optional): per-warp / per-CTA partials + one value per step
@@ -184,6 +185,51 @@ int env_int(const char *name, int dflt)
 }
 
 // ------------------------------------------------------------------ lattice launches
+constexpr size_t lat_bulk_smem(bool k3d, int stages)
+{
+    return (size_t)8 * stages * ((k3d ? 4 : 2) * 128 + 16) * sizeof(double) + (size_t)8 * stages * 8;
+}
+
+#define TK_BULK_STAGES(X) X(2) X(3) X(4) X(6)
+
+template <int WC, bool K3D, int MINB>
+int launch_lat_bulk(tk_plan *p, long long grid, cudaStream_t st, int zl_begin, int zl_end, int nsegk, int nct, int nzg)
+{
+#define X(ST)                                                                                               \
+    if (p->bulk_stages == ST) {                                                                             \
+        auto kern = tk::lat_step_bulk_kernel<WC, K3D, ST, MINB>;                                            \
+        TK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                                     (int)lat_bulk_smem(K3D, ST)));                                         \
+        kern<<<(unsigned)grid, 256, lat_bulk_smem(K3D, ST), st>>>(                                          \
+            p->lat, p->buf[p->cur], p->buf[p->cur ^ 1], p->prow, p->pcol, p->coeff, p->damping, zl_begin,   \
+            zl_end, p->rchunk, p->nchunk, nsegk, nct, nzg);                                                 \
+        p->launches++;                                                                                      \
+        TK_CUDA(cudaGetLastError());                                                                        \
+        return TK_OK;                                                                                       \
+    }
+    TK_BULK_STAGES(X)
+#undef X
+    return fail(TK_ERR_INVALID, "unsupported TK_LAT_BULK stage count %d (2, 3, 4 or 6)", p->bulk_stages);
+}
+
+template <int WC, bool K3D, int MINB>
+int lat_bulk_occ(int stages)
+{
+    int n = 0;
+#define X(ST)                                                                                               \
+    if (stages == ST) {                                                                                     \
+        auto kern = tk::lat_step_bulk_kernel<WC, K3D, ST, MINB>;                                            \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lat_bulk_smem(K3D, ST)); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 256, lat_bulk_smem(K3D, ST)) != cudaSuccess) { \
+            cudaGetLastError();                                                                             \
+            n = 1;                                                                                          \
+        }                                                                                                   \
+    }
+    TK_BULK_STAGES(X)
+#undef X
+    return std::max(n, 1);
+}
+
 template <int CPL, int WC, bool K3D, int MODE, int MINB = 1>
 int launch_lat(tk_plan *p, int zl_begin, int zl_end)
 {
@@ -207,6 +253,10 @@ int launch_lat(tk_plan *p, int zl_begin, int zl_end)
         p->lat.peer_lo = (p->push_in_kernel && p->peer_buf[0][nb])
                              ? reinterpret_cast<double *>(pptr(p, 0, nb, (p->peer_layers[0] + 1) * plane)) : nullptr;
         p->lat.peer_hi = (p->push_in_kernel && p->peer_buf[1][nb]) ? p->peer_buf[1][nb] : nullptr;
+    }
+    if constexpr (MODE == 0 && CPL == 1 && ((WC == 8 && (MINB == 3 || (K3D && MINB == 2))) || (WC == 1 && K3D && MINB == 2))) {
+        if (p->bulk_stages && !is_f32(p))
+            return launch_lat_bulk<WC, K3D, MINB>(p, grid, st, zl_begin, zl_end, nsegk, nct, nzg);
     }
     if (is_f32(p)) {
         if (CPL > 2 || MODE == 2)
@@ -805,6 +855,14 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
         p->cpl = 1;
         p->wc = 1;
     }
+    if (p->esz == 8 && !p->wz3d && env_int("TK_LAT_BULK", 0)) {  // TMA-staged variant of the default shapes
+        p->bulk_stages = env_int("TK_LAT_BULK_STAGES", halo ? 3 : 4);
+        if (p->bulk_stages != 2 && p->bulk_stages != 3 && p->bulk_stages != 4 && p->bulk_stages != 6)
+            p->bulk_stages = halo ? 3 : 4;
+        p->cpl = 1;
+        p->wc = halo ? 1 : 8;
+        p->minb = halo ? 2 : 3;
+    }
     const int nsegk_max = (int)((S + 31) / 32);
     p->nsegk = (int)((S + 32 * p->cpl - 1) / (32 * p->cpl));
     {
@@ -815,8 +873,10 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
         const long long nct = p->wz3d ? p->nsegk : (p->nsegk + p->wc - 1) / p->wc;
         const long long nzg = (Lloc + wz - 1) / wz;
         const long long slots =
-            (long long)p->sm_count * (p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d, p->minb3d)
-                                              : lat_occupancy(p->cpl, p->wc, p->minb, halo != 0));
+            (long long)p->sm_count *
+            (p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d, p->minb3d)
+                     : p->bulk_stages ? (halo ? lat_bulk_occ<1, true, 2>(p->bulk_stages) : lat_bulk_occ<8, false, 3>(p->bulk_stages))
+                                      : lat_occupancy(p->cpl, p->wc, p->minb, halo != 0));
         int best = 16;
         double best_eff = -1.0;
         // Small lattices never fill the machine: a step is then bound by the serial march of one warp
@@ -847,6 +907,7 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
 
     const int *d_seg_flag; const unsigned short *d_det_flags; const int *d_det_attr; const int2 *d_det_corr;
     const double *d_attr_im, *d_attr_v; const long long *d_ca, *d_cb; const double *d_cs;
+    seg_flag.resize(seg_flag.size() + 4, -1);  // the TMA variant fetches the aligned 16-byte quad around an entry
     TK_TRY(plan_upload(p, const_cast<int **>(&d_seg_flag), seg_flag));
     TK_TRY(plan_upload(p, const_cast<unsigned short **>(&d_det_flags), det_flags));
     TK_TRY(plan_upload(p, const_cast<int **>(&d_det_attr), det_attr));
@@ -1445,7 +1506,9 @@ int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchu
     if (wc) *wc = p->wz3d ? -p->wz3d * 100 - p->stages3d : p->wc;  // 3-D: -(100*layers_per_cta + stages)
     if (rchunk) *rchunk = p->rchunk;
     if (occ) *occ = p->wz3d ? lat3d_occupancy(p->wz3d, p->stages3d, p->minb3d)
-                            : lat_occupancy(p->cpl, p->wc, p->minb, p->lat.halo != 0);
+                    : p->bulk_stages ? (p->lat.halo ? lat_bulk_occ<1, true, 2>(p->bulk_stages)
+                                                    : lat_bulk_occ<8, false, 3>(p->bulk_stages))
+                                     : lat_occupancy(p->cpl, p->wc, p->minb, p->lat.halo != 0);
     return TK_OK;
 }
 

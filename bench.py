@@ -257,7 +257,15 @@ def gpu_single(args):
     kms = out["step_kernel_ms"]
     value = n_updates * args.steps / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
-    achieved = n_updates * bpu * args.steps / (kms * 1e-3) / 1e9
+    # Defect-free 2-D sheets advance K steps per pass (kernels_fused.cuh): a pass reads u_t, u_{t-1} and
+    # writes u_{t+K}, u_{t+K-1} = 32 B per node per pass; the remaining steps (steps mod K) move 24 B each.
+    fused = plan.fused
+    fk = fused["steps_per_pass"]
+    npass = -(-fused["fused_steps"] // fk) if fk else 0
+    nsingle = args.steps - fused["fused_steps"]
+    alg_bytes = n_updates * (npass * (4 * bpu / 3) + nsingle * bpu)
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    kernel_launches = npass + nsingle
     checksum = float(plan.get_state().sum()) if spec.num_slots <= 600_000_000 else None
 
     # e2e: the whole run through the C ABI with host buffers (kicks H2D; probe series and the final
@@ -276,6 +284,10 @@ def gpu_single(args):
            "d2h_bytes_per_step": (final.nbytes + o2["probes"].nbytes) / args.steps,
            "seconds": e2e_s, "includes": "set_state_sparse + run + probe series D2H + final state D2H (pinned)"}
     tiling = plan.tiling
+    if fk:
+        tiling = {"steps_per_pass": fk, "cells_per_lane": 1, "segs_per_cta": tiling["segs_per_cta"],
+                  "rows_per_cta": fused["rows_per_cta"], "ctas_per_sm": fused["ctas_per_sm"],
+                  "single_steps": nsingle}
     plan.close()
 
     cpu = cpu_run(workload, steps=100, warmup=2, budget_s=40.0) if not args.no_cpu else None  # ~10 s of CPU work
@@ -288,10 +300,13 @@ def gpu_single(args):
                    "l2": f"state {2 * spec.num_slots * 8 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
                    "tiling": tiling, "plan_build_s": t_build},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None if f32 else ncu_traffic(workload), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": n_updates * bpu,
-                     "kernel": "lat_step_f32_kernel" if f32 else "lat_step_kernel", "bytes_per_update": bpu,
-                     "kernel_ms_per_launch": kms / args.steps,
+                     "frac": achieved / peak,
+                     "traffic": None if f32 else ncu_traffic(workload + (f"-fused{fk}" if fk else "")),
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes / kernel_launches,
+                     "kernel": "lat_step_f32_kernel" if f32 else (f"lat_fused2d_kernel (K={fk})" if fk else "lat_step_kernel"),
+                     "bytes_per_update": alg_bytes / (n_updates * args.steps),
+                     "kernel_ms_per_launch": kms / kernel_launches,
                      "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0},
         "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),

@@ -243,3 +243,41 @@ def test_row_reordering_is_a_permutation_and_cuts_padding():
     assert reorder_rows(graph_arrays(nx.cycle_graph(100))[2], None, "auto") is None
     with pytest.raises(ValueError):
         reorder_rows(rowptr, colidx, "bogus")
+
+
+def test_fused_pass_algebra_matches_the_oracle():
+    """The derivation behind kernels_fused.cuh, restated in NumPy: on a defect-free sheet the row/column/total
+    sums follow closed recurrences, and a K-step pass = K cell-local homogeneous steps + the responses of a
+    cell at rest to the row and column forcing sequences.  Checked against the oracle's step-by-step run."""
+    from oracle import wave_oracle as wo
+
+    S, steps, K, coeff, g = 20, 45, 15, 0.04 ** 2, 0.01
+    u = np.zeros((S, S, 4))
+    u[S // 2, S // 2, 0], u[3, 5, 2] = 1.0, -0.25
+    n = S * S * 4
+    ref = wo.run_structured(S, 1, np.full(n, 3, np.uint8), np.ones(n), np.zeros(n), [], u.ravel().copy(), steps,
+                            coeff, g)
+    up = np.zeros_like(u)
+    ca, cb = (2 - g) - coeff * (2 * S + 4), -(1 - g)
+
+    def responses(X, Xp, T, Tp):
+        y, yp, out = np.zeros_like(X), np.zeros_like(X), []
+        for _ in range(K):
+            yn = ca * y + cb * yp + coeff * y.sum(1, keepdims=True) + coeff * X
+            yp, y = y, yn
+            out.append(y)
+            Xn = 2 * X - Xp + coeff * (X.sum(1, keepdims=True) + T[None, :] - (S + 4) * X) - g * (X - Xp)
+            Tn = 2 * T - Tp + coeff * (T.sum() - 4 * T) - g * (T - Tp)
+            Xp, X, Tp, T = X, Xn, T, Tn
+        return out
+
+    for _ in range(steps // K):
+        RS, CS, RSp, CSp = u.sum(1), u.sum(0), up.sum(1), up.sum(0)
+        yR = responses(RS, RSp, RS.sum(0), RSp.sum(0))
+        yC = responses(CS, CSp, RS.sum(0), RSp.sum(0))
+        for _ in range(K):
+            u, up = ca * u + cb * up + coeff * u.sum(2, keepdims=True), u
+        u = u + yR[K - 1][:, None, :] + yC[K - 1][None, :, :]
+        up = up + yR[K - 2][:, None, :] + yC[K - 2][None, :, :]
+    assert np.abs(u.ravel() - ref["u"]).max() <= 1e-13 * np.abs(ref["u"]).max()
+    assert np.abs(up.ravel() - ref["uprev"]).max() <= 1e-13 * np.abs(ref["u"]).max()

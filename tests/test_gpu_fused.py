@@ -1,0 +1,131 @@
+"""K-step fused passes on defect-free 2-D sheets (kernels_fused.cuh) against the oracle.
+
+The clique sums of a sheet without defects obey closed recurrences, so the device advances K steps per
+pass; the result must be the reference's u(t) all the same (SURVEY.md 8d config 2 is such a sheet)."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+import tetrakis_sim_b200 as tk
+from oracle import wave_oracle as wo
+from tests.helpers import rel_inf
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(S, u0, up0, steps, coeff, damping, probes):
+    n = S * S * 4
+    flags = np.full(n, 3, dtype=np.uint8)
+    return wo.run_structured(S, 1, flags, np.ones(n), np.zeros(n), [], u0.copy(), steps, coeff, damping,
+                             probes=probes, uprev0=None if up0 is None else up0.copy())
+
+
+def _run(spec, steps, kicks, damping, probes, dt=0.05):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return tk.run_wave_sim(spec, steps=steps, initial_data=kicks, c=1.0, dt=dt, damping=damping, probes=probes)
+
+
+@pytest.mark.parametrize("K", [2, 3, 8, 16, 29, 64])
+@pytest.mark.parametrize("S,steps,damping", [(1, 33, 0.0), (7, 40, 0.02), (31, 50, 0.0), (33, 37, 0.01),
+                                             (64, 64, 0.0), (150, 45, 0.03), (257, 32, 0.0)])
+def test_fused_passes_match_the_oracle(K, S, steps, damping, monkeypatch):
+    monkeypatch.setenv("TK_LAT_FUSE", str(K))
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.kick_node()
+    far = spec.node((spec.index(kick) + 4 * (S // 3) * S + 4 * (S // 5) + 2) % spec.num_slots)
+    last = spec.node(spec.num_slots - 1)
+    kicks = {kick: 1.0, far: -0.25} if far != kick else {kick: 1.0}
+    probes = [kick, far, last, spec.node(0)]
+    hist = _run(spec, steps, kicks, damping, probes)
+    assert hist.fused["steps_per_pass"] == min(K, steps)
+    assert hist.fused["fused_steps"] == (steps - 1 if steps % min(K, steps) == 1 else steps)
+    u0 = np.zeros(spec.num_slots)
+    for n_, v in kicks.items():
+        u0[spec.index(n_)] = v
+    ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, damping, [spec.index(p) for p in probes])
+    assert rel_inf(hist.final_state, ref["u"]) < 1e-12
+    assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
+
+
+@pytest.mark.parametrize("graph", ["0", "1"])
+def test_fused_passes_equal_the_step_by_step_kernel(graph, monkeypatch):
+    """Same sheet, fused vs one step per launch (direct launches and CUDA-graph replay of the pass)."""
+    monkeypatch.setenv("TK_CUDA_GRAPH", graph)
+    spec = tk.LatticeSpec(size=200, dim=2)
+    kick = spec.kick_node()
+    probes = [kick, spec.node(5), spec.node(spec.num_slots - 2)]
+    monkeypatch.setenv("TK_LAT_FUSE", "0")
+    a = _run(spec, 203, {kick: 1.0}, 0.005, probes)
+    assert a.fused["steps_per_pass"] == 0
+    monkeypatch.setenv("TK_LAT_FUSE", "8")
+    b = _run(spec, 203, {kick: 1.0}, 0.005, probes)
+    assert b.fused == {**b.fused, "steps_per_pass": 8, "fused_steps": 203}
+    assert rel_inf(b.final_state, a.final_state) < 1e-12
+    assert rel_inf(b.probe_series, a.probe_series) < 1e-12
+    assert b.metadata["launches"] < a.metadata["launches"]
+
+
+def test_fused_passes_continue_from_a_dense_state_with_a_previous_level():
+    """u_{t-1} != 0: the recurrences start from the sums of both time levels."""
+    S, steps = 48, 41
+    spec = tk.LatticeSpec(size=S, dim=2)
+    rng = np.random.default_rng(5)
+    u0 = rng.standard_normal(spec.num_slots)
+    up0 = u0 + 0.01 * rng.standard_normal(spec.num_slots)
+    coeff = 0.04 ** 2
+    plan = tk.compile_lattice(spec)
+    try:
+        plan.set_state(u0, up0)
+        out = plan.run(steps, coeff, 0.01, probes=[3, 1000])
+        assert plan.fused["steps_per_pass"] == 16 and plan.fused["fused_steps"] == 41
+        got = plan.get_state()
+        out2 = plan.run(16, coeff, 0.01, probes=[3])  # a second call continues the same simulation
+        got2 = plan.get_state()
+    finally:
+        plan.close()
+    ref = _oracle(S, u0, up0, steps, coeff, 0.01, [3, 1000])
+    assert rel_inf(got, ref["u"]) < 1e-12
+    assert rel_inf(out["probes"], ref["probes"]) < 1e-12
+    ref2 = _oracle(S, u0, up0, steps + 16, coeff, 0.01, [3])
+    assert rel_inf(got2, ref2["u"]) < 1e-12
+    assert rel_inf(out2["probes"], ref2["probes"][steps:]) < 1e-12
+
+
+def test_fusion_is_not_used_where_the_recurrences_do_not_close(monkeypatch):
+    """Defects, 3-D, full history, energy series: step by step."""
+    monkeypatch.setenv("TK_LAT_FUSE", "8")
+    hole = tk.LatticeSpec(size=40, dim=2, defect="blackhole", radius=3.0)
+    assert _run(hole, 32, None, 0.0, None).fused["steps_per_pass"] == 0
+    wedge = tk.LatticeSpec(size=40, dim=2, defect="wedge")
+    assert _run(wedge, 32, None, 0.0, None).fused["steps_per_pass"] == 0
+    cube = tk.LatticeSpec(size=16, dim=3, layers=4)
+    assert _run(cube, 32, None, 0.0, None).fused["steps_per_pass"] == 0
+    sheet = tk.LatticeSpec(size=40, dim=2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        full = tk.run_wave_sim(sheet, steps=32, dt=0.05, record="all")
+        en = tk.run_wave_sim(tk.LatticeSpec(size=256, dim=2), steps=32, dt=0.05, energy=True)
+    assert full.fused["steps_per_pass"] == 0 and en.fused["steps_per_pass"] == 0
+    assert _run(sheet, 32, None, 0.0, None).fused["steps_per_pass"] == 8
+    assert _run(sheet, 1, None, 0.0, None).fused["steps_per_pass"] == 0
+    many = [sheet.node(i) for i in range(9)]  # more probes than a pass can record
+    assert _run(sheet, 32, None, 0.0, many).fused["steps_per_pass"] == 0
+
+
+def test_fused_long_run_stays_within_the_parity_bar():
+    """2 000 steps at the clamped (marginally stable) dt on 256^2: 1e-10 relative on u and the probe."""
+    S, steps = 256, 2000
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.kick_node()
+    hist = _run(spec, steps, {kick: 1.0}, 0.0, [kick], dt=0.1)
+    assert hist.metadata["stability_adjusted"] and hist.fused["steps_per_pass"] == 16
+    u0 = np.zeros(spec.num_slots)
+    u0[spec.index(kick)] = 1.0
+    ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, 0.0, [spec.index(kick)])
+    assert rel_inf(hist.final_state, ref["u"]) < 1e-10
+    assert rel_inf(hist.probe_series, ref["probes"]) < 1e-10
+    freq, spectrum, _ = tk.run_fft(hist, kick)
+    assert wo.folded_bin(spectrum) == wo.folded_bin(wo.run_fft(ref["probes"][:, 0], hist.dt)[1])

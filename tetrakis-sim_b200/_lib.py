@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "tk_graph_plan_create", "tk_lattice_plan_create", "tk_lattice_plan_create_ex",
     "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
-    "tk_plan_run", "tk_plan_set_probes", "tk_plan_read_probes", "tk_plan_launch_count", "tk_plan_destroy",
+    "tk_plan_run", "tk_plan_set_probes", "tk_plan_read_probes", "tk_plan_launch_count", "tk_plan_fused_info", "tk_plan_destroy",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
     "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
     "tk_lattice_ipc_export", "tk_ipc_open", "tk_ipc_close", "tk_lattice_peer_attach",
@@ -107,6 +107,7 @@ def lib():
     L.tk_plan_set_probes.argtypes = [P, c_int64, P, c_int64]
     L.tk_plan_read_probes.argtypes = [P, P, POINTER(c_int64)]
     L.tk_plan_launch_count.argtypes = [P, POINTER(c_int64)]
+    L.tk_plan_fused_info.argtypes = [P, POINTER(c_int32), POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]
     L.tk_plan_destroy.argtypes = [P]
     L.tk_lattice_halo_ptrs.argtypes = [P, c_int32, POINTER(P), POINTER(P), POINTER(P), POINTER(P),
                                        POINTER(c_int64)]  # fmt: skip
@@ -256,6 +257,13 @@ class Plan:
         n = c_int64(0)
         check(lib().tk_plan_launch_count(self._h, ctypes.byref(n)))
         return n.value
+
+    @property
+    def fused(self) -> dict:
+        """How the last run() went: steps per fused pass (0 = step by step), steps covered by passes."""
+        k, n, r, o = c_int32(0), c_int64(0), c_int32(0), c_int32(0)
+        check(lib().tk_plan_fused_info(self._h, ctypes.byref(k), ctypes.byref(n), ctypes.byref(r), ctypes.byref(o)))
+        return {"steps_per_pass": k.value, "fused_steps": n.value, "rows_per_cta": r.value, "ctas_per_sm": o.value}
 
     @property
     def tiling(self) -> dict:

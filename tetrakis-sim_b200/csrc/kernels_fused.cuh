@@ -1,0 +1,226 @@
+// K leapfrog steps in ONE pass over the state, for defect-free 2-D sheets.
+//
+// On a sheet without defects every row/column clique is complete and all nodes share one degree
+// (2S+1), mass and potential, so the clique sums obey their own closed recurrences
+// (reference operator: tetrakis_sim/lattice.py:30-73, update: tetrakis_sim/physics.py:119-126):
+//
+//   lap(r,c,q)  = cell(r,c) + RS[r,q] + CS[c,q] - (2S+4) u
+//   RS+[r,q]    = 2 RS - RS- + coeff (RT[r] + Tot[q] - (S+4) RS[r,q]) - g (RS - RS-),  RT[r]  = sum_q RS[r,q]
+//   CS+[c,q]    = 2 CS - CS- + coeff (CT[c] + Tot[q] - (S+4) CS[c,q]) - g (CS - CS-),  CT[c]  = sum_q CS[c,q]
+//   Tot+[q]     = 2 Tot - Tot- + coeff (TT - 4 Tot[q]) - g (Tot - Tot-),               TT     = sum_q Tot[q]
+//
+// i.e. the sums of steps t+1 .. t+K-1 are known without touching the state.  Given them, a node's
+// update only needs its own cell:  u+ = ca u + cb u- + coeff cell + coeff RS[r] + coeff CS[c],
+// ca = (2-g) - coeff (2S+4), cb = -(1-g).  The update is linear, so the pass splits it:
+//   * every lane steps its own cell K times WITHOUT the line terms (registers only), and
+//   * the contribution of the line terms -- the response y of a cell at rest to the forcing sequence
+//     coeff RS_k[r] (resp. coeff CS_k[c]), stepped with the same cell recurrence -- is computed once
+//     per row / column line by lat_tables_kernel and added at the end of the pass.
+// A pass reads u_t, u_{t-1} and writes u_{t+K}, u_{t+K-1} in place: 32/K bytes per node update
+// instead of 24.  It also produces the exact partial row/column sums of both written states, so the
+// next pass restarts every recurrence from sums of the real data.
+#pragma once
+#include "common.cuh"
+
+namespace tk {
+
+constexpr int kFusedMaxProbes = 8;
+struct FusedProbes {
+    int n;
+    int q[kFusedMaxProbes];
+    long long cell[kFusedMaxProbes];  // r*S + c of the probe's cell
+};
+
+// Quadrant totals of the current and previous state from the finalised row sums, fixed summation order.
+// tot[0..3] = Tot_t[q], tot[4..7] = Tot_{t-1}[q].
+__global__ void __launch_bounds__(1024)
+lat_totals_kernel(int S, const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
+                  double *__restrict__ tot)
+{
+    __shared__ double red[2][1024];
+    const int t = threadIdx.x, q = t & 3;
+    double a = 0.0, b = 0.0;
+    for (int r = t >> 2; r < S; r += 256) {
+        a += rowinfo[(size_t)r * 8 + q];
+        b += rowinfo_prev[(size_t)r * 8 + q];
+    }
+    red[0][t] = a;
+    red[1][t] = b;
+    __syncthreads();
+    for (int o = 512; o >= 4; o >>= 1) {
+        if (t < o) {
+            red[0][t] += red[0][t + o];
+            red[1][t] += red[1][t + o];
+        }
+        __syncthreads();
+    }
+    if (t < 4) {
+        tot[t] = red[0][t];
+        tot[4 + t] = red[1][t];
+    }
+}
+
+// One thread per row or column line.  Advances the line's four quadrant sums X_k (k = 0..K-1) with the
+// recurrences above and, alongside, the response y of a cell at rest to the forcing coeff * X_k:
+//   y_{k+1} = ca y_k + cb y_{k-1} + coeff sum_q y_k + coeff X_k,   y_0 = y_{-1} = 0.
+// resp[line][k][q] = y_{k+1}[q]; the pass adds y_K to u_{t+K} and y_{K-1} to u_{t+K-1} (and y_{k+1}
+// to a probe's value at step t+k+1).
+__global__ void __launch_bounds__(128)
+lat_tables_kernel(int S, int K, double coeff, double damping, double ca, double cb,
+                  const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
+                  const double *__restrict__ colinfo, const double *__restrict__ colinfo_prev,
+                  const double *__restrict__ tot, double *__restrict__ respR, double *__restrict__ respC)
+{
+    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= 2 * S) return;
+    const bool is_col = line >= S;
+    const int idx = is_col ? line - S : line;
+    const double *src = (is_col ? colinfo : rowinfo) + (size_t)idx * 8;
+    const double *srcp = (is_col ? colinfo_prev : rowinfo_prev) + (size_t)idx * 8;
+    double *dst = (is_col ? respC : respR) + (size_t)idx * K * 4;
+    double X[4], Xp[4], T[4], Tp[4], y[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        X[q] = src[q];
+        Xp[q] = srcp[q];
+        T[q] = tot[q];
+        Tp[q] = tot[4 + q];
+    }
+    const double s4 = (double)S + 4.0;
+    for (int k = 0; k < K; ++k) {
+        const double yc = coeff * ((y[0] + y[1]) + (y[2] + y[3]));
+        const double XT = (X[0] + X[1]) + (X[2] + X[3]);
+        const double TT = (T[0] + T[1]) + (T[2] + T[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double yn = fma(ca, y[q], fma(cb, yp[q], yc)) + coeff * X[q];
+            yp[q] = y[q];
+            y[q] = yn;
+            dst[k * 4 + q] = yn;
+            const double xn = 2.0 * X[q] - Xp[q] + coeff * ((XT + T[q]) - s4 * X[q]) - damping * (X[q] - Xp[q]);
+            const double tn = 2.0 * T[q] - Tp[q] + coeff * (TT - 4.0 * T[q]) - damping * (T[q] - Tp[q]);
+            Xp[q] = X[q];
+            X[q] = xn;
+            Tp[q] = T[q];
+            T[q] = tn;
+        }
+    }
+}
+
+// The pass.  CTA = WC = blockDim/32 adjacent 32-cell segments marching down `rchunk` rows, one cell
+// per lane (256-bit loads/stores), like lat_step_kernel.  Shared memory holds the two response vectors
+// (y_K, y_{K-1}) of the CTA's rows and columns: (rows + columns) x 64 bytes, whatever K is.
+//   ua: in u_t,     out u_{t+K}      ub: in u_{t-1}, out u_{t+K-1}
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+lat_fused2d_kernel(int S, int K, double *__restrict__ ua, double *__restrict__ ub, const double *__restrict__ respR,
+                   const double *__restrict__ respC, double *__restrict__ prow_a, double *__restrict__ pcol_a,
+                   double *__restrict__ prow_b, double *__restrict__ pcol_b, double ca, double cb, double coeff,
+                   int rchunk, int nchunk, int nsegk, int nct, int pf_rows,
+                   const __grid_constant__ FusedProbes probes, double *__restrict__ probe_series,
+                   const long long *__restrict__ ctr, long long row0)
+{
+    extern __shared__ __align__(16) unsigned char tk_smem[];
+    const int WC = blockDim.x >> 5;
+    const int ncol = WC * 32;
+    double *colresp = reinterpret_cast<double *>(tk_smem);  // [4 parts: a01 a23 b01 b23][ncol][2]: lanes 16 B apart
+    double *rowresp = colresp + (size_t)ncol * 8;            // [row][a0..a3 b0..b3]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ct = blockIdx.x % nct;
+    const int ch = blockIdx.x / nct;
+    const int r_begin = ch * rchunk;
+    const int r_end = min(S, r_begin + rchunk);
+    const int col0 = ct * ncol;
+    // j = 0..3: y_K[q] (added to u_{t+K}); j = 4..7: y_{K-1}[q] (added to u_{t+K-1}; zero when K = 1)
+    for (int i = threadIdx.x; i < ncol * 8; i += blockDim.x) {
+        const int cl_ = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
+        const int c = col0 + cl_;
+        const double v = (c < S && k >= 0) ? respC[((size_t)c * K + k) * 4 + q] : 0.0;
+        colresp[((size_t)(j >> 1) * ncol + cl_) * 2 + (j & 1)] = v;
+    }
+    for (int i = threadIdx.x; i < (r_end - r_begin) * 8; i += blockDim.x) {
+        const int rl = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
+        rowresp[i] = k >= 0 ? respR[((size_t)(r_begin + rl) * K + k) * 4 + q] : 0.0;
+    }
+    __syncthreads();
+
+    const int segk = ct * WC + warp;
+    if (segk >= nsegk) return;
+    const int cl = warp * 32 + lane;
+    const int c0 = col0 + cl;
+    const bool valid = c0 < S;
+    long long base_row = row0;
+    if (ctr != nullptr) base_row = ctr[0];
+    double cacc_a[4] = {0, 0, 0, 0}, cacc_b[4] = {0, 0, 0, 0};
+    for (int r = r_begin; r < r_end; ++r) {
+        const size_t off = ((size_t)r * S + c0) * 4;
+        double u[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0};
+        if (valid) {
+            ld256_cs(ua + off, u);
+            ld256_cs(ub + off, up);
+            if (pf_rows > 0 && r + pf_rows < r_end && (lane & 3) == 0) {
+                prefetch_l2(ua + off + (size_t)pf_rows * S * 4);
+                prefetch_l2(ub + off + (size_t)pf_rows * S * 4);
+            }
+        }
+        bool hit = false;
+        for (int p = 0; p < probes.n; ++p) hit |= valid && probes.cell[p] == (long long)r * S + c0;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const double cc = coeff * ((u[0] + u[1]) + (u[2] + u[3]));
+            double un[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) un[q] = fma(ca, u[q], fma(cb, up[q], cc));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                up[q] = u[q];
+                u[q] = un[q];
+            }
+            if (hit) {
+                for (int p = 0; p < probes.n; ++p)
+                    if (probes.cell[p] == (long long)r * S + c0) {
+                        const int pq = probes.q[p];
+                        const double h = pq == 0 ? u[0] : (pq == 1 ? u[1] : (pq == 2 ? u[2] : u[3]));
+                        probe_series[(size_t)(base_row + k) * probes.n + p] =
+                            h + (respR[((size_t)r * K + k) * 4 + pq] + respC[((size_t)c0 * K + k) * 4 + pq]);
+                    }
+            }
+        }
+        {
+            const double *rr = rowresp + (size_t)(r - r_begin) * 8;
+            const double2 ra01 = *reinterpret_cast<const double2 *>(rr);
+            const double2 ra23 = *reinterpret_cast<const double2 *>(rr + 2);
+            const double2 rb01 = *reinterpret_cast<const double2 *>(rr + 4);
+            const double2 rb23 = *reinterpret_cast<const double2 *>(rr + 6);
+            const double2 ca01 = *reinterpret_cast<const double2 *>(colresp + ((size_t)0 * ncol + cl) * 2);
+            const double2 ca23 = *reinterpret_cast<const double2 *>(colresp + ((size_t)1 * ncol + cl) * 2);
+            const double2 cb01 = *reinterpret_cast<const double2 *>(colresp + ((size_t)2 * ncol + cl) * 2);
+            const double2 cb23 = *reinterpret_cast<const double2 *>(colresp + ((size_t)3 * ncol + cl) * 2);
+            u[0] += ra01.x + ca01.x;  u[1] += ra01.y + ca01.y;  u[2] += ra23.x + ca23.x;  u[3] += ra23.y + ca23.y;
+            up[0] += rb01.x + cb01.x; up[1] += rb01.y + cb01.y; up[2] += rb23.x + cb23.x; up[3] += rb23.y + cb23.y;
+        }
+        if (valid) {
+            st256_cs(ua + off, u);
+            st256_cs(ub + off, up);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                u[q] = 0.0;
+                up[q] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            cacc_a[q] += u[q];
+            cacc_b[q] += up[q];
+        }
+        warp_sum4_store(u, lane, prow_a + ((size_t)r * nsegk + segk) * 4);
+        warp_sum4_store(up, lane, prow_b + ((size_t)r * nsegk + segk) * 4);
+    }
+    if (valid) {
+        st256(pcol_a + ((size_t)ch * S + c0) * 4, cacc_a);
+        st256(pcol_b + ((size_t)ch * S + c0) * 4, cacc_b);
+    }
+}
+
+}  // namespace tk

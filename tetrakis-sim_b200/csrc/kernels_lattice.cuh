@@ -1001,9 +1001,9 @@ __global__ void history_row_kernel(const void *__restrict__ src, int src_is_f32,
 }
 
 // End of a replayed step: advance the row counters (probes, history, energy).
-__global__ void advance_kernel(long long *ctr)
+__global__ void advance_kernel(long long *ctr, int inc)
 {
-    if (threadIdx.x < 3) ctr[threadIdx.x] += 1;
+    if (threadIdx.x < 3) ctr[threadIdx.x] += inc;
 }
 
 }  // namespace tk

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels_ensemble.cuh"
+#include "kernels_fused.cuh"
 #include "kernels_graph.cuh"
 #include "kernels_lattice.cuh"
 
@@ -136,6 +137,15 @@ struct tk_plan {
     int minb = 1;                            // register path: min resident CTAs per SM asked of ptxas
     int layers_global = 1, z_begin = 0;
     double coeff = 0.0, damping = 0.0;
+    // K-step fused passes (defect-free 2-D sheets, kernels_fused.cuh)
+    bool plain2d = false;                    // eligible: one layer, no defect records, fp64
+    int fuse_k = 0, fuse_minb = 3;           // largest K the response tables were sized for (0 = not set up)
+    int fuse_k_run = 0;                      // steps per pass of the last tk_plan_run
+    int fuse_wc = 8, fuse_rchunk = 0, fuse_nchunk = 0, fuse_nsegk = 0, fuse_occ = 0;
+    double *tabR = nullptr, *tabC = nullptr, *rowinfo_prev = nullptr, *colinfo_prev = nullptr;
+    double *prow_b = nullptr, *fpcol_a = nullptr, *fpcol_b = nullptr, *ftot = nullptr;
+    std::vector<long long> probe_idx_host;   // buffer-relative probe indices (fused passes write probes)
+    long long fused_steps_last = 0;          // steps the last tk_plan_run advanced with fused passes
     std::vector<long long> dead_local;  // ABI-local indices of removed nodes (for dense set_state)
 };
 
@@ -410,6 +420,20 @@ int lat_occupancy(int cpl, int wc, int mb, bool k3d)
     return 2;
 }
 
+int lat_finalise_sums(tk_plan *p, const double *prow, const double *pcol, int nsegk, int nchunk, double *rowinfo,
+                      double *colinfo)
+{
+    const long long nline = (long long)p->lat.Lloc * p->lat.S;
+    const int nrowblk = (int)((nline + 7) / 8);
+    const int ncolblk = (int)((nline * 4 + 31) / 32);
+    tk::lat_finalise_kernel<<<(unsigned)(nrowblk + ncolblk), 256, 0, p->stream>>>(
+        p->lat.S, p->lat.Lloc, nsegk, nchunk, nrowblk, prow, pcol, rowinfo, colinfo, nullptr, 0, nullptr, 0,
+        nullptr, nullptr, 0, nullptr, nullptr);
+    p->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TK_OK;
+}
+
 int lat_finalise(tk_plan *p, const double *state, double *probe_row)
 {
     const long long nline = (long long)p->lat.Lloc * p->lat.S;
@@ -469,6 +493,7 @@ int set_probes(tk_plan *p, long long n_probes, const int64_t *idx, long long row
 {
     p->n_probes = 0;
     p->probe_row = 0;
+    p->probe_idx_host.clear();
     if (p->probe_idx) { cudaFree(p->probe_idx); p->probe_idx = nullptr; }
     if (p->probe_series) { cudaFree(p->probe_series); p->probe_series = nullptr; }
     if (n_probes <= 0) return TK_OK;
@@ -483,6 +508,135 @@ int set_probes(tk_plan *p, long long n_probes, const int64_t *idx, long long row
     TK_CUDA(cudaMalloc((void **)&p->probe_series, (size_t)rows * n_probes * sizeof(double)));
     p->n_probes = (int)n_probes;
     p->probe_rows_cap = rows;
+    p->probe_idx_host = h;
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------ K-step fused passes (2-D, no defects)
+#define TK_CHK(x)          \
+    do {                   \
+        const int rc_ = (x); \
+        if (rc_) return rc_; \
+    } while (0)
+
+size_t fuse_smem(int wc, int rows) { return ((size_t)wc * 32 + rows) * 8 * sizeof(double); }
+
+template <int MB>
+int fuse_occ_one(int wc, int rows)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tk::lat_fused2d_kernel<MB>, wc * 32, fuse_smem(wc, rows)) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        n = 1;
+    }
+    return std::max(n, 1);
+}
+
+int fuse_occupancy(int mb, int wc, int rows)
+{
+    return mb == 2 ? fuse_occ_one<2>(wc, rows) : (mb == 4 ? fuse_occ_one<4>(wc, rows) : fuse_occ_one<3>(wc, rows));
+}
+
+// Steps per pass for this run (0 = step by step).  TK_LAT_FUSE: 0/1 off, else steps per pass.
+int fuse_choice(const tk_plan *p, const tk_run_args *a)
+{
+    if (p->kind != kLattice || !p->plain2d || a->history_out || a->energy_out) return 0;
+    if (a->n_probes > tk::kFusedMaxProbes) return 0;
+    const int k = std::min<int64_t>(env_int("TK_LAT_FUSE", 16), a->steps);
+    return k >= 2 ? k : 0;
+}
+
+int fuse_setup(tk_plan *p, int k)
+{
+    if (p->fuse_k >= k) return TK_OK;  // tables are sized for the largest K seen; shorter passes reuse them
+    const int S = p->lat.S;
+    int mb = env_int("TK_LAT_FUSE_MINB", 4);
+    if (mb < 2 || mb > 4) mb = 3;
+    const int nseg32 = (S + 31) / 32;
+    const int wc = nseg32 >= 8 ? 8 : (nseg32 >= 2 ? 2 : 1);
+    const int nct = (nseg32 + wc - 1) / wc;
+    // rows per CTA: the same trade as the step kernel -- per-CTA response/partial traffic against whole
+    // waves of (SMs x resident CTAs); two partial-sum sets are written per pass
+    const int rc_cap = 128;
+    const int occ = fuse_occupancy(mb, wc, rc_cap);
+    const long long slots = (long long)p->sm_count * occ;
+    int best = 16;
+    double best_eff = -1.0;
+    if ((long long)((S + 15) / 16) * nct < slots) {
+        const long long want = std::max<long long>(1, slots / std::max(1, nct));
+        best = (int)std::max<long long>(4, std::min<long long>((S + want - 1) / want, 16));
+    } else {
+        for (int rc_ = 16; rc_ <= rc_cap && rc_ <= std::max(16, S); ++rc_) {
+            const long long tiles = (long long)((S + rc_ - 1) / rc_) * nct;
+            const long long waves = (tiles + slots - 1) / slots;
+            const double eff = (double)tiles / (double)(waves * slots) * (1.0 / (1.0 + 2.0 / rc_));
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = rc_; }
+        }
+    }
+    int rchunk = env_int("TK_LAT_FUSE_RCHUNK", best);
+    if (rchunk < 1 || rchunk > rc_cap) rchunk = best;
+    const int nchunk = (S + rchunk - 1) / rchunk;
+    TK_CHK(plan_alloc(p, &p->tabR, (size_t)S * k * 4, true));
+    TK_CHK(plan_alloc(p, &p->tabC, (size_t)S * k * 4, true));
+    if (!p->rowinfo_prev) {
+        TK_CHK(plan_alloc(p, &p->rowinfo_prev, (size_t)S * 8, true));
+        TK_CHK(plan_alloc(p, &p->colinfo_prev, (size_t)S * 8, true));
+        TK_CHK(plan_alloc(p, &p->prow_b, (size_t)S * nseg32 * 4, true));
+        TK_CHK(plan_alloc(p, &p->ftot, 8, true));
+        TK_CHK(plan_alloc(p, &p->fpcol_a, (size_t)nchunk * S * 4, true));
+        TK_CHK(plan_alloc(p, &p->fpcol_b, (size_t)nchunk * S * 4, true));
+        p->fuse_minb = mb; p->fuse_wc = wc; p->fuse_rchunk = rchunk; p->fuse_nchunk = nchunk;
+        p->fuse_nsegk = nseg32; p->fuse_occ = occ;
+    }
+    p->fuse_k = k;
+    return TK_OK;
+}
+
+// Row/column sums of u_{t-1} (the recurrences need two time levels); the sums of u_t are current.
+int fuse_prepare(tk_plan *p)
+{
+    p->cur ^= 1;
+    const int rc = launch_lat_dispatch<1>(p, 0, p->lat.Lloc);
+    p->cur ^= 1;
+    if (rc) return rc;
+    return lat_finalise_sums(p, p->prow, p->pcol, p->nsegk, p->nchunk, p->rowinfo_prev, p->colinfo_prev);
+}
+
+// One pass = k steps.  buf[cur] stays u_t's buffer (it receives u_{t+k}), buf[cur^1] receives u_{t+k-1}.
+int fuse_pass(tk_plan *p, int k, cudaEvent_t ev_begin, cudaEvent_t ev_end)
+{
+    const int S = p->lat.S, wc = p->fuse_wc;
+    const int nct = (p->fuse_nsegk + wc - 1) / wc;
+    tk::FusedProbes pr{};
+    pr.n = p->n_probes;
+    for (int i = 0; i < p->n_probes; ++i) {
+        pr.cell[i] = p->probe_idx_host[i] >> 2;
+        pr.q[i] = (int)(p->probe_idx_host[i] & 3);
+    }
+    const double g = p->damping;
+    const double ca = (2.0 - g) - p->coeff * (2.0 * S + 4.0), cb = -(1.0 - g);
+    tk::lat_totals_kernel<<<1, 1024, 0, p->stream>>>(S, p->rowinfo, p->rowinfo_prev, p->ftot);
+    tk::lat_tables_kernel<<<(unsigned)((2 * S + 127) / 128), 128, 0, p->stream>>>(
+        S, k, p->coeff, g, ca, cb, p->rowinfo, p->rowinfo_prev, p->colinfo, p->colinfo_prev, p->ftot, p->tabR, p->tabC);
+    const unsigned grid = (unsigned)(p->fuse_nchunk * nct);
+    const size_t sm = fuse_smem(wc, p->fuse_rchunk);
+    if (ev_begin) TK_CUDA(cudaEventRecord(ev_begin, p->stream));
+#define TK_FUSE_LAUNCH(MB)                                                                                      \
+    tk::lat_fused2d_kernel<MB><<<grid, wc * 32, sm, p->stream>>>(                                               \
+        S, k, p->buf[p->cur], p->buf[p->cur ^ 1], p->tabR, p->tabC, p->prow, p->fpcol_a, p->prow_b, p->fpcol_b, ca, cb, \
+        p->coeff, p->fuse_rchunk, p->fuse_nchunk, p->fuse_nsegk, nct, p->pf_rows, pr, p->probe_series,          \
+        p->ctr_mode ? p->ctr_dev : nullptr, p->probe_row)
+    if (p->fuse_minb == 2) TK_FUSE_LAUNCH(2);
+    else if (p->fuse_minb == 4) TK_FUSE_LAUNCH(4);
+    else TK_FUSE_LAUNCH(3);
+#undef TK_FUSE_LAUNCH
+    if (ev_end) TK_CUDA(cudaEventRecord(ev_end, p->stream));
+    p->launches += 3;
+    TK_CUDA(cudaGetLastError());
+    TK_CHK(lat_finalise_sums(p, p->prow, p->fpcol_a, p->fuse_nsegk, p->fuse_nchunk, p->rowinfo, p->colinfo));
+    TK_CHK(lat_finalise_sums(p, p->prow_b, p->fpcol_b, p->fuse_nsegk, p->fuse_nchunk, p->rowinfo_prev, p->colinfo_prev));
+    if (!p->ctr_mode && p->n_probes > 0) p->probe_row += k;
     return TK_OK;
 }
 
@@ -855,6 +1009,7 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
         p->cpl = 1;
         p->wc = 1;
     }
+    p->plain2d = halo == 0 && Lloc == 1 && ndet == 0 && corr.empty() && p->esz == 8;
     if (p->esz == 8 && !p->wz3d && env_int("TK_LAT_BULK", 0)) {  // TMA-staged variant of the default shapes
         p->bulk_stages = env_int("TK_LAT_BULK_STAGES", halo ? 3 : 4);
         if (p->bulk_stages != 2 && p->bulk_stages != 3 && p->bulk_stages != 4 && p->bulk_stages != 6)
@@ -1241,8 +1396,71 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     // launches are identical every time.  Large lattices gain nothing (their kernels take ~1 ms) and the
     // per-kernel event timing cannot be captured, so both keep the direct launches below.
     int64_t steps_left = a->steps;
+    size_t kev_used = 0;      // event pairs recorded
+    int64_t kev_steps = 0;    // steps those pairs cover
+    p->fused_steps_last = 0;
+
+    // ---- defect-free 2-D sheets: K steps per pass over the state (kernels_fused.cuh); the remainder
+    // (steps mod K) runs step by step below
+    const int fk = fuse_choice(p, a);
+    if (fk > 1 && steps_left >= fk) {
+        TK_RUN_TRY(fuse_setup(p, fk));
+        TK_RUN_TRY(fuse_prepare(p));
+        p->fuse_k_run = fk;
+        const int64_t npass = steps_left / fk;
+        const bool fgraph = npass >= 4 && !a->step_kernel_ms && p->n <= (1LL << 24) && env_int("TK_CUDA_GRAPH", 1) != 0;
+        if (fgraph) {
+            if (!p->ctr_dev) TK_RUN_CUDA(cudaMalloc((void **)&p->ctr_dev, 4 * sizeof(long long)));
+            const long long ctr0[4] = {p->probe_row, 0, 0, 0};
+            TK_RUN_CUDA(cudaMemcpyAsync(p->ctr_dev, ctr0, sizeof(ctr0), cudaMemcpyHostToDevice, p->stream));
+            TK_RUN_CUDA(cudaStreamSynchronize(p->stream));
+            p->ctr_mode = true;
+            const long long launches_before = p->launches;
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            cudaError_t ce = cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal);
+            int rcap = TK_OK;
+            if (ce == cudaSuccess) {
+                rcap = fuse_pass(p, fk, nullptr, nullptr);
+                if (rcap == TK_OK) {
+                    tk::advance_kernel<<<1, 32, 0, p->stream>>>(p->ctr_dev, fk);
+                    p->launches++;
+                }
+                ce = cudaStreamEndCapture(p->stream, &graph);
+            }
+            if (ce == cudaSuccess && rcap == TK_OK) ce = cudaGraphInstantiate(&exec, graph, 0);
+            const long long per_pass = p->launches - launches_before;
+            for (int64_t i = 0; i < npass && ce == cudaSuccess && rcap == TK_OK; ++i) ce = cudaGraphLaunch(exec, p->stream);
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            p->ctr_mode = false;
+            if (ce != cudaSuccess || rcap != TK_OK) {
+                if (d_hist) cudaFree(d_hist);
+                if (rcap != TK_OK) return rcap;
+                return fail(TK_ERR_CUDA, "CUDA graph of the fused pass failed: %s", cudaGetErrorString(ce));
+            }
+            p->launches = launches_before + per_pass * npass;
+            if (p->n_probes > 0) p->probe_row += npass * fk;
+        } else {
+            for (int64_t i = 0; i < npass; ++i) {
+                const bool tk_ = kev_used + 2 <= kev.size();
+                TK_RUN_TRY(fuse_pass(p, fk, tk_ ? kev[kev_used] : nullptr, tk_ ? kev[kev_used + 1] : nullptr));
+                if (tk_) { kev_used += 2; kev_steps += fk; }
+            }
+        }
+        steps_left -= npass * fk;
+        p->fused_steps_last = npass * fk;
+        if (steps_left >= 2) {  // the remainder as one shorter pass (a single left-over step runs below)
+            const int kr = (int)steps_left;
+            const bool tk_ = kev_used + 2 <= kev.size();
+            TK_RUN_TRY(fuse_pass(p, kr, tk_ ? kev[kev_used] : nullptr, tk_ ? kev[kev_used + 1] : nullptr));
+            if (tk_) { kev_used += 2; kev_steps += kr; }
+            p->fused_steps_last += kr;
+            steps_left = 0;
+        }
+    }
     const bool hist_in_one_chunk = !d_hist || (hist_stride == 1 && chunk_rows >= a->steps + 1);
-    const bool use_graph = a->steps >= 8 && !a->step_kernel_ms && hist_in_one_chunk && p->n <= (1LL << 24) &&
+    const bool use_graph = steps_left >= 8 && !a->step_kernel_ms && hist_in_one_chunk && p->n <= (1LL << 24) &&
                            env_int("TK_CUDA_GRAPH", 1) != 0;
     if (use_graph) {
         if (!p->ctr_dev) {
@@ -1261,7 +1479,7 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
                                                                   d_hist, p->n, p->ctr_dev);
                 p->launches++;
             }
-            tk::advance_kernel<<<1, 32, 0, p->stream>>>(p->ctr_dev);
+            tk::advance_kernel<<<1, 32, 0, p->stream>>>(p->ctr_dev, 1);
             p->launches++;
             return cudaGetLastError() == cudaSuccess ? TK_OK : fail(TK_ERR_CUDA, "graph-mode launch failed");
         };
@@ -1285,10 +1503,10 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
             if (rcap != TK_OK) return rcap;
             return fail(TK_ERR_CUDA, "CUDA graph capture failed: %s", cudaGetErrorString(ce));
         }
-        const int64_t pairs = a->steps / 2;
+        const int64_t pairs = steps_left / 2;
         for (int64_t i = 0; i < pairs && ce == cudaSuccess; ++i) ce = cudaGraphLaunch(exec, p->stream);
         p->launches = launches_before + per_pair * pairs;
-        if (ce == cudaSuccess && (a->steps & 1)) {
+        if (ce == cudaSuccess && (steps_left & 1)) {
             const int r = one_step();
             if (r) ce = cudaErrorUnknown;
         }
@@ -1299,25 +1517,27 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
             if (d_hist) cudaFree(d_hist);
             return fail(TK_ERR_CUDA, "CUDA graph replay failed: %s", cudaGetErrorString(ce));
         }
-        p->probe_row += p->n_probes > 0 ? a->steps : 0;
-        p->energy_row += p->energy_on ? a->steps : 0;
-        if (d_hist) hist_fill += a->steps;
+        p->probe_row += p->n_probes > 0 ? steps_left : 0;
+        p->energy_row += p->energy_on ? steps_left : 0;
+        if (d_hist) hist_fill += steps_left;
         steps_left = 0;
     }
     if (p->kind == kGraph) {
         for (int64_t s = 0; s < steps_left; ++s) {
-            const bool tk_ = (size_t)(2 * s + 1) < kev.size();
-            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s], p->stream));
+            const bool tk_ = kev_used + 2 <= kev.size();
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[kev_used], p->stream));
             TK_RUN_TRY(graph_step(p, a->coeff, a->damping));
-            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s + 1], p->stream));
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[kev_used + 1], p->stream));
+            if (tk_) { kev_used += 2; kev_steps += 1; }
             TK_RUN_CUDA(record());
         }
     } else {
         for (int64_t s = 0; s < steps_left; ++s) {
-            const bool tk_ = (size_t)(2 * s + 1) < kev.size();
-            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s], p->stream));
+            const bool tk_ = kev_used + 2 <= kev.size();
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[kev_used], p->stream));
             TK_RUN_TRY(tk_lattice_step_layers(p, 0, p->lat.Lloc));
-            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[2 * s + 1], p->stream));
+            if (tk_) TK_RUN_CUDA(cudaEventRecord(kev[kev_used + 1], p->stream));
+            if (tk_) { kev_used += 2; kev_steps += 1; }
             TK_RUN_TRY(tk_lattice_step_end(p));
             TK_RUN_CUDA(record());
         }
@@ -1343,13 +1563,13 @@ int tk_plan_run(tk_plan *p, const tk_run_args *a)
     }
     if (a->step_kernel_ms) {
         double total = 0.0;
-        for (size_t i = 0; i + 1 < kev.size(); i += 2) {
+        for (size_t i = 0; i + 1 < kev_used; i += 2) {
             float ms = 0.f;
             TK_RUN_CUDA(cudaEventElapsedTime(&ms, kev[i], kev[i + 1]));
             total += ms;
         }
         // scale to all steps if the pool was smaller than the step count
-        if (!kev.empty()) total *= (double)a->steps / (double)(kev.size() / 2);
+        if (kev_steps > 0) total *= (double)a->steps / (double)kev_steps;
         *a->step_kernel_ms = total;
         for (auto &e : kev) cudaEventDestroy(e);
     }
@@ -1509,6 +1729,17 @@ int tk_lattice_tiling(const tk_plan *p, int32_t *cpl, int32_t *wc, int32_t *rchu
                     : p->bulk_stages ? (p->lat.halo ? lat_bulk_occ<1, true, 2>(p->bulk_stages)
                                                     : lat_bulk_occ<8, false, 3>(p->bulk_stages))
                                      : lat_occupancy(p->cpl, p->wc, p->minb, p->lat.halo != 0);
+    return TK_OK;
+}
+
+int tk_plan_fused_info(tk_plan *p, int32_t *steps_per_pass, int64_t *fused_steps, int32_t *rows_per_cta,
+                       int32_t *ctas_per_sm)
+{
+    TK_REQUIRE(p, "NULL plan");
+    if (steps_per_pass) *steps_per_pass = p->fused_steps_last > 0 ? p->fuse_k_run : 0;
+    if (fused_steps) *fused_steps = p->fused_steps_last;
+    if (rows_per_cta) *rows_per_cta = p->fuse_rchunk;
+    if (ctas_per_sm) *ctas_per_sm = p->fuse_occ;
     return TK_OK;
 }
 

@@ -217,6 +217,7 @@ def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device,
         hist.elapsed_ms = out["elapsed_ms"]
         hist.energy = None if out["energy"] is None else out["energy"] * (c * c)
         hist.metadata["launches"] = plan.launches
+        hist.fused = plan.fused  # defect-free 2-D sheets advance K steps per pass (tk_plan_fused_info)
         return hist
     finally:
         plan.close()

@@ -209,12 +209,33 @@ def pinned_empty(n):
     return t, t.numpy()
 
 
-def gpu_single(args):
+def gpu_single(args, dist=None, emit=True):
+    """One lattice per GPU.  N = 1: the bench line.  N > 1 (``dist`` given): N independent replicas of the same
+    sheet, one per rank -- a 2-D sheet does not shard ("replicas only"), so there is no data-path
+    collective; the timed region is bracketed by barriers and the slowest rank's device time counts."""
     import torch
 
     import tetrakis_sim_b200 as tk
 
+    rank = int(os.environ.get("RANK", "0")) if dist else 0
+    world = int(os.environ.get("WORLD_SIZE", "1")) if dist else 1
+    local = int(os.environ.get("LOCAL_RANK", str(rank))) if dist else 0
     torch.cuda.init()
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+
+    def fence():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     workload = args.workload or "cfg2-2d-8192"
     if workload == "cfg2-2d-8192":
         spec = tk.LatticeSpec(size=args.size or 8192, dim=2)
@@ -234,7 +255,7 @@ def gpu_single(args):
     f32 = args.dtype == "f32"
     bpu = BYTES_PER_UPDATE / 2 if f32 else BYTES_PER_UPDATE
     t_build = time.perf_counter()
-    plan = tk.compile_lattice(spec, device=0, dtype="float32" if f32 else "float64")
+    plan = tk.compile_lattice(spec, device=local, dtype="float32" if f32 else "float64")
     maxdeg = plan.max_degree
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build  # graph-to-device compile (excluded from every rate below)
@@ -244,18 +265,19 @@ def gpu_single(args):
     n_updates = spec.num_nodes  # surviving nodes
     kidx = [spec.index(kick)]
 
-    clk = ClockSampler(0).start()
+    clk = ClockSampler(local).start()
     plan.set_state_sparse(kidx, [1.0])
     plan.run(args.warmup, coeff, 0.0, probes=kidx)
-    torch.cuda.synchronize()
+    fence()
     l0 = plan.launches
     with clk:
+        fence()
         out = plan.run(args.steps, coeff, 0.0, probes=kidx, timed=True, kernel_timing=True)
-        torch.cuda.synchronize()
+        fence()
     launches = plan.launches - l0
-    ms = out["elapsed_ms"]
+    ms = max_over_ranks(out["elapsed_ms"])  # device time (CUDA events on the plan's stream), slowest rank
     kms = out["step_kernel_ms"]
-    value = n_updates * args.steps / (ms * 1e-3) / 1e9
+    value = world * n_updates * args.steps / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
     # Defect-free 2-D sheets advance K steps per pass (kernels_fused.cuh): a pass reads u_t, u_{t-1} and
     # writes u_{t+K}, u_{t+K-1} = 32 B per node per pass; the remaining steps (steps mod K) move 24 B each.
@@ -272,16 +294,16 @@ def gpu_single(args):
     # state D2H into pinned host memory), device-synchronised wall clock
     hold, final = pinned_empty(plan.num_nodes)
     from tetrakis_sim_b200 import _lib
-    torch.cuda.synchronize()
+    fence()
     t0 = time.perf_counter()
     plan.set_state_sparse(kidx, [1.0])
     o2 = plan.run(args.steps, coeff, 0.0, probes=kidx)
     _lib.check(_lib.lib().tk_plan_get_state(plan._h, _lib._p(final), None))
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e = {"value": n_updates * args.steps / e2e_s / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": 16.0 / args.steps,
-           "d2h_bytes_per_step": (final.nbytes + o2["probes"].nbytes) / args.steps,
+    fence()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * n_updates * args.steps / e2e_s / 1e9, "unit": UNIT,
+           "h2d_bytes_per_step": world * 16.0 / args.steps,
+           "d2h_bytes_per_step": world * (final.nbytes + o2["probes"].nbytes) / args.steps,
            "seconds": e2e_s, "includes": "set_state_sparse + run + probe series D2H + final state D2H (pinned)"}
     tiling = plan.tiling
     if fk:
@@ -290,18 +312,23 @@ def gpu_single(args):
                   "single_steps": nsingle}
     plan.close()
 
-    cpu = cpu_run(workload, steps=100, warmup=2, budget_s=40.0) if not args.no_cpu else None  # ~10 s of CPU work
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cpu = cpu_run(workload, steps=100, warmup=2, budget_s=40.0)  # ~10 s of CPU work
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": workload, "lattice": desc.replace("fp64", "fp32 state (fp64 sums)") if f32 else desc, "nodes": n_updates, "max_degree": maxdeg,
                    "effective_dt": dt_eff, "kick": list(map(str, kick)),
                    "l2": f"state {2 * spec.num_slots * 8 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
-                   "tiling": tiling, "plan_build_s": t_build},
+                   "tiling": tiling, "plan_build_s": t_build,
+                   "parallelism": "single GPU" if world == 1 else
+                   f"{world} independent replicas of the sheet, one per GPU, no data-path collective (a 2-D sheet "
+                   "does not shard; the sharded 3-D slab run of the same launch is reported under sharded_3d)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     "traffic": None if f32 else ncu_traffic(workload + (f"-fused{fk}" if fk else "")),
+                     "traffic": None if f32 else ncu_traffic(workload + ("-fused" if fk else "")),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes / kernel_launches,
                      "kernel": "lat_step_f32_kernel" if f32 else (f"lat_fused2d_kernel (K={fk})" if fk else "lat_step_kernel"),
@@ -314,8 +341,9 @@ def gpu_single(args):
         "checksum_sum_u": checksum,
         "checksum_expected": float(args.warmup + args.steps + 1) if spec.defect != "singularity" else None,
     }
-    print(json.dumps(line))
-    return 0
+    if emit and rank == 0:
+        print(json.dumps(line))
+    return line
 
 
 def gpu_ensemble(args):
@@ -415,10 +443,33 @@ def main():
     if args.workload == "cfg5-ensemble":
         return gpu_ensemble(args)
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        return gpu_single(args)
+        gpu_single(args)
+        return 0
     from tetrakis_sim_b200.slab import bench_slabs  # multi-GPU: layer slabs + halo exchange
 
-    return bench_slabs(args)
+    if args.workload is not None and args.workload != "cfg2-2d-8192":
+        return bench_slabs(args)
+    # N > 1, the metric's own configuration: one replica of the sheet per GPU (same workload as N = 1, weak
+    # scaling), followed in the same launch by the layer-slab run of the 3-D lattice that does shard
+    import torch
+    import torch.distributed as dist
+
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    line = gpu_single(args, dist=dist, emit=False)
+    slab = None
+    if args.workload is None:
+        slab = bench_slabs(args, emit=False)
+    elif dist.is_initialized():
+        dist.destroy_process_group()
+    if rank == 0:
+        if slab is not None:
+            line["sharded_3d"] = {k: slab[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "e2e",
+                                                       "gpu_launches", "single_gpu_same_workload",
+                                                       "checksum_sum_u", "checksum_expected")}
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":

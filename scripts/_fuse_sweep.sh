@@ -1,8 +1,6 @@
 set -x
-timeout 1500 python -m pytest tests/test_gpu_fused.py -q -x 2>&1 | tail -15
-for cfg in "4 3" "8 3" "16 3" "16 2" "16 4" "24 3" "32 3" "32 4" "48 3" "64 3"; do
-  set -- $cfg
-  echo "== cfg2 fuse K=$1 minb=$2"; TK_LAT_FUSE=$1 TK_LAT_FUSE_MINB=$2 timeout 300 python bench.py --steps 384 --warmup 16 --no-cpu 2>&1 | tail -1
-done
-echo "== K=16 pf sweep"
-for pf in 0 2; do echo "== pf $pf"; TK_LAT_PREFETCH=$pf TK_LAT_FUSE=16 timeout 300 python bench.py --steps 384 --warmup 16 --no-cpu 2>&1 | tail -1; done
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+python bench.py --no-cpu 2>&1 | tail -1
+python bench.py --steps 1000 --warmup 48 --no-cpu 2>&1 | tail -1
+TK_LAT_FUSE=32 python bench.py --steps 1024 --warmup 32 --no-cpu 2>&1 | tail -1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_cfg2_fused.csv python bench.py --steps 192 --warmup 48 --no-cpu > gpurun_out/ncu_l.log 2>&1

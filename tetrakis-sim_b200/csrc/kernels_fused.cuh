@@ -16,6 +16,8 @@
 //   * the contribution of the line terms -- the response y of a cell at rest to the forcing sequence
 //     coeff RS_k[r] (resp. coeff CS_k[c]), stepped with the same cell recurrence -- is computed once
 //     per row / column line by lat_tables_kernel and added at the end of the pass.
+// The lane steps its cell in the cell's eigenbasis (mean + three deviations: four independent scalar
+// recurrences, 4 FP64 instructions per cell and step when damping = 0, 8 otherwise).
 // A pass reads u_t, u_{t-1} and writes u_{t+K}, u_{t+K-1} in place: 32/K bytes per node update
 // instead of 24.  It also produces the exact partial row/column sums of both written states, so the
 // next pass restarts every recurrence from sums of the real data.
@@ -31,32 +33,116 @@ struct FusedProbes {
     long long cell[kFusedMaxProbes];  // r*S + c of the probe's cell
 };
 
-// Quadrant totals of the current and previous state from the finalised row sums, fixed summation order.
-// tot[0..3] = Tot_t[q], tot[4..7] = Tot_{t-1}[q].
-__global__ void __launch_bounds__(1024)
-lat_totals_kernel(int S, const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
-                  double *__restrict__ tot)
+// Row/column sums of a sheet that is zero except for n <= 64 distinct kicks (tk_plan_set_state_sparse):
+// one thread per (line, quadrant) adds the kicks of its line in kick order.  idx = node index (r*S+c)*4+q.
+// info_prev (optional) gets zeros: the previous level of a freshly kicked state is empty.
+__global__ void __launch_bounds__(256)
+lat_sparse_sums_kernel(int S, int n, const long long *__restrict__ idx, const double *__restrict__ val,
+                       double *__restrict__ rowinfo, double *__restrict__ colinfo)
 {
-    __shared__ double red[2][1024];
-    const int t = threadIdx.x, q = t & 3;
-    double a = 0.0, b = 0.0;
-    for (int r = t >> 2; r < S; r += 256) {
-        a += rowinfo[(size_t)r * 8 + q];
-        b += rowinfo_prev[(size_t)r * 8 + q];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * S * 4) return;
+    const int q = t & 3, line = (t >> 2) % S;
+    const bool is_col = (t >> 2) >= S;
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const long long cell = idx[i] >> 2;
+        const int kq = (int)(idx[i] & 3), r = (int)(cell / S), c = (int)(cell % S);
+        if (kq == q && (is_col ? c : r) == line) a += val[i];
     }
-    red[0][t] = a;
-    red[1][t] = b;
-    __syncthreads();
-    for (int o = 512; o >= 4; o >>= 1) {
-        if (t < o) {
-            red[0][t] += red[0][t + o];
-            red[1][t] += red[1][t + o];
+    (is_col ? colinfo : rowinfo)[(size_t)line * 8 + q] = a;
+}
+
+__global__ void __launch_bounds__(256) lat_zero_sums_kernel(int S, double *__restrict__ rowinfo, double *__restrict__ colinfo)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * S * 4) return;
+    ((t >> 2) >= S ? colinfo : rowinfo)[(size_t)((t >> 2) % S) * 8 + (t & 3)] = 0.0;
+}
+
+// Per-block quadrant totals (8 consecutive rows per block, fixed order) of both time levels from the
+// finalised row sums: totpart[lvl][blk][q].  Only needed when a run enters the fused mode; afterwards
+// lat_finalise2_kernel produces them as a by-product.
+__global__ void __launch_bounds__(256)
+lat_totparts_kernel(int S, int nblk, const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
+                    double *__restrict__ totpart)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * nblk * 4) return;
+    const int q = t & 3, blk = (t >> 2) % nblk, lvl = (t >> 2) / nblk;
+    const double *src = lvl ? rowinfo_prev : rowinfo;
+    double a = 0.0;
+    for (int r = blk * 8; r < min(S, blk * 8 + 8); ++r) a += src[(size_t)r * 8 + q];
+    totpart[((size_t)lvl * nblk + blk) * 4 + q] = a;
+}
+
+// Finalise BOTH states a pass has written, in one launch: fixed-order sums of the row partials (one warp per
+// row line) and of the column partials (8 chunk slices per CTA), as lat_finalise_kernel does for one state,
+// plus the per-block quadrant totals the next lat_tables_kernel starts from.
+// grid = 2 * (nrowblk + ncolblk); first half = state a (u_{t+K}), second half = state b (u_{t+K-1}).
+__global__ void __launch_bounds__(256)
+lat_finalise2_kernel(int S, int nsegk, int nchunk, int nrowblk, int ncolblk, const double *__restrict__ prow_a,
+                     const double *__restrict__ pcol_a, const double *__restrict__ prow_b,
+                     const double *__restrict__ pcol_b, double *__restrict__ rowinfo_a, double *__restrict__ colinfo_a,
+                     double *__restrict__ rowinfo_b, double *__restrict__ colinfo_b, double *__restrict__ totpart)
+{
+    __shared__ double part[8][32];
+    const int half = nrowblk + ncolblk;
+    const int lvl = (int)blockIdx.x >= half ? 1 : 0;
+    const int blk = (int)blockIdx.x - lvl * half;
+    const double *prow = lvl ? prow_b : prow_a, *pcol = lvl ? pcol_b : pcol_a;
+    double *rowinfo = lvl ? rowinfo_b : rowinfo_a, *colinfo = lvl ? colinfo_b : colinfo_a;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (blk < nrowblk) {
+        const int line = blk * 8 + w;
+        double acc = 0.0;
+        if (line < S) {
+            const double *p = prow + (size_t)line * nsegk * 4;
+            const int len = nsegk * 4;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int i = lane;
+            for (; i + 96 < len; i += 128) {
+                a0 += p[i];
+                a1 += p[i + 32];
+                a2 += p[i + 64];
+                a3 += p[i + 96];
+            }
+            for (; i < len; i += 32) a0 += p[i];
+            acc = (a0 + a1) + (a2 + a3);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (lane < 4) rowinfo[(size_t)line * 8 + lane] = acc;
         }
+        if (lane < 4) part[w][lane] = acc;
         __syncthreads();
-    }
-    if (t < 4) {
-        tot[t] = red[0][t];
-        tot[4 + t] = red[1][t];
+        if (threadIdx.x < 4) {
+            const int q = threadIdx.x;
+            totpart[((size_t)lvl * nrowblk + blk) * 4 + q] =
+                ((part[0][q] + part[1][q]) + (part[2][q] + part[3][q])) + ((part[4][q] + part[5][q]) + (part[6][q] + part[7][q]));
+        }
+    } else {
+        const long long t = (long long)(blk - nrowblk) * 32 + lane;
+        double acc = 0.0;
+        if (t < (long long)S * 4) {
+            const double *p = pcol + t;
+            const size_t stride = (size_t)S * 4;
+            double a0 = 0.0, a1 = 0.0;
+            int k = w;
+            for (; k + 8 < nchunk; k += 16) {
+                a0 += p[(size_t)k * stride];
+                a1 += p[(size_t)(k + 8) * stride];
+            }
+            if (k < nchunk) a0 += p[(size_t)k * stride];
+            acc = a0 + a1;
+        }
+        part[w][lane] = acc;
+        __syncthreads();
+        if (w == 0 && t < (long long)S * 4) {
+            const double s01 = part[0][lane] + part[1][lane], s23 = part[2][lane] + part[3][lane];
+            const double s45 = part[4][lane] + part[5][lane], s67 = part[6][lane] + part[7][lane];
+            colinfo[(t >> 2) * 8 + (t & 3)] = (s01 + s23) + (s45 + s67);
+        }
     }
 }
 
@@ -69,8 +155,28 @@ __global__ void __launch_bounds__(128)
 lat_tables_kernel(int S, int K, double coeff, double damping, double ca, double cb,
                   const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
                   const double *__restrict__ colinfo, const double *__restrict__ colinfo_prev,
-                  const double *__restrict__ tot, double *__restrict__ respR, double *__restrict__ respC)
+                  const double *__restrict__ totpart, int nblk, double *__restrict__ respR, double *__restrict__ respC)
 {
+    // quadrant totals of both time levels: every CTA sums the per-block totals in the same fixed order
+    __shared__ double red[2][128];
+    {
+        const int t = threadIdx.x, q = t & 3;
+        double a = 0.0, b = 0.0;
+        for (int blk = t >> 2; blk < nblk; blk += 32) {
+            a += totpart[(size_t)blk * 4 + q];
+            b += totpart[((size_t)nblk + blk) * 4 + q];
+        }
+        red[0][t] = a;
+        red[1][t] = b;
+        __syncthreads();
+        for (int o = 64; o >= 4; o >>= 1) {
+            if (t < o) {
+                red[0][t] += red[0][t + o];
+                red[1][t] += red[1][t + o];
+            }
+            __syncthreads();
+        }
+    }
     const int line = blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= 2 * S) return;
     const bool is_col = line >= S;
@@ -83,8 +189,8 @@ lat_tables_kernel(int S, int K, double coeff, double damping, double ca, double 
     for (int q = 0; q < 4; ++q) {
         X[q] = src[q];
         Xp[q] = srcp[q];
-        T[q] = tot[q];
-        Tp[q] = tot[4 + q];
+        T[q] = red[0][q];
+        Tp[q] = red[1][q];
     }
     const double s4 = (double)S + 4.0;
     for (int k = 0; k < K; ++k) {
@@ -111,7 +217,7 @@ lat_tables_kernel(int S, int K, double coeff, double damping, double ca, double 
 // per lane (256-bit loads/stores), like lat_step_kernel.  Shared memory holds the two response vectors
 // (y_K, y_{K-1}) of the CTA's rows and columns: (rows + columns) x 64 bytes, whatever K is.
 //   ua: in u_t,     out u_{t+K}      ub: in u_{t-1}, out u_{t+K-1}
-template <int MINB>
+template <int MINB, bool UNDAMPED>
 __global__ void __launch_bounds__(256, MINB)
 lat_fused2d_kernel(int S, int K, double *__restrict__ ua, double *__restrict__ ub, const double *__restrict__ respR,
                    const double *__restrict__ respC, double *__restrict__ prow_a, double *__restrict__ pcol_a,
@@ -151,6 +257,7 @@ lat_fused2d_kernel(int S, int K, double *__restrict__ ua, double *__restrict__ u
     const bool valid = c0 < S;
     long long base_row = row0;
     if (ctr != nullptr) base_row = ctr[0];
+    const double lam_m = ca + 4.0 * coeff;
     double cacc_a[4] = {0, 0, 0, 0}, cacc_b[4] = {0, 0, 0, 0};
     for (int r = r_begin; r < r_end; ++r) {
         const size_t off = ((size_t)r * S + c0) * 4;
@@ -164,28 +271,56 @@ lat_fused2d_kernel(int S, int K, double *__restrict__ ua, double *__restrict__ u
             }
         }
         bool hit = false;
+#pragma unroll 1
         for (int p = 0; p < probes.n; ++p) hit |= valid && probes.cell[p] == (long long)r * S + c0;
-#pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-            const double cc = coeff * ((u[0] + u[1]) + (u[2] + u[3]));
-            double un[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) un[q] = fma(ca, u[q], fma(cb, up[q], cc));
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                up[q] = u[q];
-                u[q] = un[q];
-            }
-            if (hit) {
-                for (int p = 0; p < probes.n; ++p)
-                    if (probes.cell[p] == (long long)r * S + c0) {
-                        const int pq = probes.q[p];
-                        const double h = pq == 0 ? u[0] : (pq == 1 ? u[1] : (pq == 2 ? u[2] : u[3]));
-                        probe_series[(size_t)(base_row + k) * probes.n + p] =
-                            h + (respR[((size_t)r * K + k) * 4 + pq] + respC[((size_t)c0 * K + k) * 4 + pq]);
-                    }
+        // Cell eigenbasis: the cell operator ca*I + coeff*J (J = all-ones 4x4) acts as (ca + 4 coeff) on the
+        // cell mean m and as ca on the deviations d_q = u_q - m (d_3 = -(d_0+d_1+d_2)), so K steps are four
+        // independent scalar recurrences y+ = lam*y + cb*y-: one FMA per recurrence and step when damping = 0
+        // (cb = -1), an FMA and a multiply otherwise.
+        double m = 0.25 * ((u[0] + u[1]) + (u[2] + u[3])), mp = 0.25 * ((up[0] + up[1]) + (up[2] + up[3]));
+        double d0 = u[0] - m, d1 = u[1] - m, d2 = u[2] - m;
+        double e0 = up[0] - mp, e1 = up[1] - mp, e2 = up[2] - mp;
+#define TK_FUSED_STEP()                          \
+    do {                                         \
+        double mn, n0, n1, n2;                   \
+        if (UNDAMPED) {                          \
+            mn = fma(lam_m, m, -mp);             \
+            n0 = fma(ca, d0, -e0);               \
+            n1 = fma(ca, d1, -e1);               \
+            n2 = fma(ca, d2, -e2);               \
+        } else {                                 \
+            mn = fma(lam_m, m, cb * mp);         \
+            n0 = fma(ca, d0, cb * e0);           \
+            n1 = fma(ca, d1, cb * e1);           \
+            n2 = fma(ca, d2, cb * e2);           \
+        }                                        \
+        mp = m; m = mn;                          \
+        e0 = d0; d0 = n0;                        \
+        e1 = d1; d1 = n1;                        \
+        e2 = d2; d2 = n2;                        \
+    } while (0)
+        if (!__any_sync(0xffffffffu, hit)) {
+#pragma unroll 8
+            for (int k = 0; k < K; ++k) TK_FUSED_STEP();
+        } else {  // a probe's cell is in this warp's segment of the row (rare): record it after every step
+#pragma unroll 1
+            for (int k = 0; k < K; ++k) {
+                TK_FUSED_STEP();
+                if (hit) {
+#pragma unroll 1
+                    for (int p = 0; p < probes.n; ++p)
+                        if (probes.cell[p] == (long long)r * S + c0) {
+                            const int pq = probes.q[p];
+                            const double dq = pq == 0 ? d0 : (pq == 1 ? d1 : (pq == 2 ? d2 : -((d0 + d1) + d2)));
+                            probe_series[(size_t)(base_row + k) * probes.n + p] =
+                                (m + dq) + (respR[((size_t)r * K + k) * 4 + pq] + respC[((size_t)c0 * K + k) * 4 + pq]);
+                        }
+                }
             }
         }
+#undef TK_FUSED_STEP
+        u[0] = m + d0; u[1] = m + d1; u[2] = m + d2; u[3] = m - ((d0 + d1) + d2);
+        up[0] = mp + e0; up[1] = mp + e1; up[2] = mp + e2; up[3] = mp - ((e0 + e1) + e2);
         {
             const double *rr = rowresp + (size_t)(r - r_begin) * 8;
             const double2 ra01 = *reinterpret_cast<const double2 *>(rr);

@@ -141,6 +141,9 @@ struct tk_plan {
     bool plain2d = false;                    // eligible: one layer, no defect records, fp64
     int fuse_k = 0, fuse_minb = 3;           // largest K the response tables were sized for (0 = not set up)
     int fuse_k_run = 0;                      // steps per pass of the last tk_plan_run
+    // which finalised sums are current (plain 2-D sheets only; lets a run skip the sums-only passes)
+    bool sums_cur_valid = false;             // rowinfo/colinfo hold the sums of buf[cur]
+    int sums_prev = 0;                       // rowinfo_prev/colinfo_prev: 0 unknown, 1 valid, 2 buf[cur^1] is all zero
     int fuse_wc = 8, fuse_rchunk = 0, fuse_nchunk = 0, fuse_nsegk = 0, fuse_occ = 0;
     double *tabR = nullptr, *tabC = nullptr, *rowinfo_prev = nullptr, *colinfo_prev = nullptr;
     double *prow_b = nullptr, *fpcol_a = nullptr, *fpcol_b = nullptr, *ftot = nullptr;
@@ -525,7 +528,7 @@ template <int MB>
 int fuse_occ_one(int wc, int rows)
 {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tk::lat_fused2d_kernel<MB>, wc * 32, fuse_smem(wc, rows)) !=
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tk::lat_fused2d_kernel<MB, false>, wc * 32, fuse_smem(wc, rows)) !=
         cudaSuccess) {
         cudaGetLastError();
         n = 1;
@@ -543,13 +546,16 @@ int fuse_choice(const tk_plan *p, const tk_run_args *a)
 {
     if (p->kind != kLattice || !p->plain2d || a->history_out || a->energy_out) return 0;
     if (a->n_probes > tk::kFusedMaxProbes) return 0;
-    const int k = std::min<int64_t>(env_int("TK_LAT_FUSE", 16), a->steps);
+    // default: the largest K at which the pass is still HBM-bound on a B200 (FP64 pipe ~60 % busy): the cell
+    // recurrences cost 4 FP64 instructions per cell and step without damping, 8 with
+    const int k = std::min<int64_t>(env_int("TK_LAT_FUSE", a->damping == 0.0 ? 48 : 24), a->steps);
     return k >= 2 ? k : 0;
 }
 
 int fuse_setup(tk_plan *p, int k)
 {
     if (p->fuse_k >= k) return TK_OK;  // tables are sized for the largest K seen; shorter passes reuse them
+    k = std::max(k, 64);               // (cudaMalloc is slow: do not grow them run by run)
     const int S = p->lat.S;
     int mb = env_int("TK_LAT_FUSE_MINB", 4);
     if (mb < 2 || mb > 4) mb = 3;
@@ -583,7 +589,7 @@ int fuse_setup(tk_plan *p, int k)
         TK_CHK(plan_alloc(p, &p->rowinfo_prev, (size_t)S * 8, true));
         TK_CHK(plan_alloc(p, &p->colinfo_prev, (size_t)S * 8, true));
         TK_CHK(plan_alloc(p, &p->prow_b, (size_t)S * nseg32 * 4, true));
-        TK_CHK(plan_alloc(p, &p->ftot, 8, true));
+        TK_CHK(plan_alloc(p, &p->ftot, (size_t)2 * ((S + 7) / 8) * 4, true));  // per-block quadrant totals, 2 levels
         TK_CHK(plan_alloc(p, &p->fpcol_a, (size_t)nchunk * S * 4, true));
         TK_CHK(plan_alloc(p, &p->fpcol_b, (size_t)nchunk * S * 4, true));
         p->fuse_minb = mb; p->fuse_wc = wc; p->fuse_rchunk = rchunk; p->fuse_nchunk = nchunk;
@@ -596,11 +602,24 @@ int fuse_setup(tk_plan *p, int k)
 // Row/column sums of u_{t-1} (the recurrences need two time levels); the sums of u_t are current.
 int fuse_prepare(tk_plan *p)
 {
-    p->cur ^= 1;
-    const int rc = launch_lat_dispatch<1>(p, 0, p->lat.Lloc);
-    p->cur ^= 1;
-    if (rc) return rc;
-    return lat_finalise_sums(p, p->prow, p->pcol, p->nsegk, p->nchunk, p->rowinfo_prev, p->colinfo_prev);
+    if (p->sums_prev == 2) {
+        tk::lat_zero_sums_kernel<<<(unsigned)((2 * p->lat.S * 4 + 255) / 256), 256, 0, p->stream>>>(
+            p->lat.S, p->rowinfo_prev, p->colinfo_prev);
+        p->launches++;
+    } else if (p->sums_prev != 1) {
+        p->cur ^= 1;
+        const int rc = launch_lat_dispatch<1>(p, 0, p->lat.Lloc);
+        p->cur ^= 1;
+        if (rc) return rc;
+        TK_CHK(lat_finalise_sums(p, p->prow, p->pcol, p->nsegk, p->nchunk, p->rowinfo_prev, p->colinfo_prev));
+    }
+    p->sums_prev = 1;
+    const int nblk = (p->lat.S + 7) / 8;
+    tk::lat_totparts_kernel<<<(unsigned)((2 * nblk * 4 + 255) / 256), 256, 0, p->stream>>>(
+        p->lat.S, nblk, p->rowinfo, p->rowinfo_prev, p->ftot);
+    p->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TK_OK;
 }
 
 // One pass = k steps.  buf[cur] stays u_t's buffer (it receives u_{t+k}), buf[cur^1] receives u_{t+k-1}.
@@ -616,27 +635,37 @@ int fuse_pass(tk_plan *p, int k, cudaEvent_t ev_begin, cudaEvent_t ev_end)
     }
     const double g = p->damping;
     const double ca = (2.0 - g) - p->coeff * (2.0 * S + 4.0), cb = -(1.0 - g);
-    tk::lat_totals_kernel<<<1, 1024, 0, p->stream>>>(S, p->rowinfo, p->rowinfo_prev, p->ftot);
+    const int nrowblk = (S + 7) / 8, ncolblk = (S * 4 + 31) / 32;
     tk::lat_tables_kernel<<<(unsigned)((2 * S + 127) / 128), 128, 0, p->stream>>>(
-        S, k, p->coeff, g, ca, cb, p->rowinfo, p->rowinfo_prev, p->colinfo, p->colinfo_prev, p->ftot, p->tabR, p->tabC);
+        S, k, p->coeff, g, ca, cb, p->rowinfo, p->rowinfo_prev, p->colinfo, p->colinfo_prev, p->ftot, nrowblk, p->tabR,
+        p->tabC);
     const unsigned grid = (unsigned)(p->fuse_nchunk * nct);
     const size_t sm = fuse_smem(wc, p->fuse_rchunk);
     if (ev_begin) TK_CUDA(cudaEventRecord(ev_begin, p->stream));
-#define TK_FUSE_LAUNCH(MB)                                                                                      \
-    tk::lat_fused2d_kernel<MB><<<grid, wc * 32, sm, p->stream>>>(                                               \
+#define TK_FUSE_LAUNCH1(MB, UD)                                                                                 \
+    tk::lat_fused2d_kernel<MB, UD><<<grid, wc * 32, sm, p->stream>>>(                                           \
         S, k, p->buf[p->cur], p->buf[p->cur ^ 1], p->tabR, p->tabC, p->prow, p->fpcol_a, p->prow_b, p->fpcol_b, ca, cb, \
         p->coeff, p->fuse_rchunk, p->fuse_nchunk, p->fuse_nsegk, nct, p->pf_rows, pr, p->probe_series,          \
         p->ctr_mode ? p->ctr_dev : nullptr, p->probe_row)
+#define TK_FUSE_LAUNCH(MB)              \
+    do {                                \
+        if (g == 0.0) TK_FUSE_LAUNCH1(MB, true);  \
+        else TK_FUSE_LAUNCH1(MB, false);          \
+    } while (0)
     if (p->fuse_minb == 2) TK_FUSE_LAUNCH(2);
     else if (p->fuse_minb == 4) TK_FUSE_LAUNCH(4);
     else TK_FUSE_LAUNCH(3);
 #undef TK_FUSE_LAUNCH
+#undef TK_FUSE_LAUNCH1
     if (ev_end) TK_CUDA(cudaEventRecord(ev_end, p->stream));
+    tk::lat_finalise2_kernel<<<(unsigned)(2 * (nrowblk + ncolblk)), 256, 0, p->stream>>>(
+        S, p->fuse_nsegk, p->fuse_nchunk, nrowblk, ncolblk, p->prow, p->fpcol_a, p->prow_b, p->fpcol_b, p->rowinfo,
+        p->colinfo, p->rowinfo_prev, p->colinfo_prev, p->ftot);
     p->launches += 3;
     TK_CUDA(cudaGetLastError());
-    TK_CHK(lat_finalise_sums(p, p->prow, p->fpcol_a, p->fuse_nsegk, p->fuse_nchunk, p->rowinfo, p->colinfo));
-    TK_CHK(lat_finalise_sums(p, p->prow_b, p->fpcol_b, p->fuse_nsegk, p->fuse_nchunk, p->rowinfo_prev, p->colinfo_prev));
     if (!p->ctr_mode && p->n_probes > 0) p->probe_row += k;
+    p->sums_cur_valid = true;
+    p->sums_prev = 1;
     return TK_OK;
 }
 
@@ -1144,6 +1173,8 @@ int tk_plan_set_state_sparse(tk_plan *p, int64_t n, const int64_t *index, const 
     TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * p->esz, p->stream));
     TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * p->esz, p->stream));
     p->cur = 0;
+    p->sums_cur_valid = false;
+    p->sums_prev = 2;  // u_{t-1} = 0
     if (n > 0) {
         std::vector<long long> h(n);
         for (int64_t i = 0; i < n; ++i) {
@@ -1166,6 +1197,18 @@ int tk_plan_set_state_sparse(tk_plan *p, int64_t n, const int64_t *index, const 
             p->launches++;
             e = cudaGetLastError();
         }
+        // a defect-free sheet with a handful of distinct kicks: the row/column sums follow from the kicks
+        bool distinct = p->kind == kLattice && p->plain2d && n <= 64;
+        for (int64_t i = 0; distinct && i < n; ++i)
+            for (int64_t j = 0; j < i; ++j)
+                if (h[i] == h[j]) { distinct = false; break; }
+        if (e == cudaSuccess && distinct) {
+            tk::lat_sparse_sums_kernel<<<(unsigned)((2 * p->lat.S * 4 + 255) / 256), 256, 0, p->stream>>>(
+                p->lat.S, (int)n, d_idx, d_val, p->rowinfo, p->colinfo);
+            p->launches++;
+            e = cudaGetLastError();
+            p->sums_cur_valid = e == cudaSuccess;
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
         cudaFree(d_idx);
         cudaFree(d_val);
@@ -1178,6 +1221,8 @@ int tk_plan_set_state(tk_plan *p, const double *u, const double *u_prev)
 {
     TK_REQUIRE(p && u, "NULL argument");
     TK_CUDA(cudaSetDevice(p->device));
+    p->sums_cur_valid = false;
+    p->sums_prev = u_prev ? 0 : 2;
     TK_CUDA(cudaMemsetAsync(p->buf[0], 0, (size_t)p->alloc * p->esz, p->stream));
     TK_CUDA(cudaMemsetAsync(p->buf[1], 0, (size_t)p->alloc * p->esz, p->stream));
     p->cur = 0;
@@ -1265,9 +1310,20 @@ int tk_lattice_step_begin(tk_plan *p, double coeff, double damping)
     TK_CUDA(cudaSetDevice(p->device));
     p->coeff = coeff;
     p->damping = damping;
+    if (p->plain2d && p->sums_cur_valid) {  // the sums of u_t are current: only the probes' row 0 is due
+        if (double *row = next_probe_row(p)) {
+            tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(
+                p->buf[p->cur], p->probe_idx, row, p->n_probes, nullptr);
+            p->launches++;
+            TK_CUDA(cudaGetLastError());
+        }
+        return TK_OK;
+    }
     int rc = launch_lat_dispatch<1>(p, 0, p->lat.Lloc);
     if (rc) return rc;
-    return lat_finalise(p, p->buf[p->cur], next_probe_row(p));
+    rc = lat_finalise(p, p->buf[p->cur], next_probe_row(p));
+    p->sums_cur_valid = rc == TK_OK;
+    return rc;
 }
 
 int tk_lattice_step_layers(tk_plan *p, int32_t zl_begin, int32_t zl_end)
@@ -1300,6 +1356,7 @@ int tk_lattice_step_layers_on(tk_plan *p, int32_t zl_begin, int32_t zl_end, void
 int tk_lattice_step_end(tk_plan *p)
 {
     TK_REQUIRE(p && p->kind == kLattice, "not a lattice plan");
+    p->sums_prev = 0;  // rowinfo now describes the new state; the old sums are gone
     p->cur ^= 1;
     return lat_finalise(p, p->buf[p->cur], next_probe_row(p));
 }

@@ -323,7 +323,7 @@ def global_max_degree(plan_max: int, dist, device=None) -> int:
 # ------------------------------------------------------------------------------------------------
 # bench.py --gpus N (N > 1): weak scaling, 64 layers of 1024x1024 per GPU (BASELINE configs[2])
 # ------------------------------------------------------------------------------------------------
-def bench_slabs(args) -> int:
+def bench_slabs(args, emit: bool = True):
     import torch
     import torch.distributed as dist
 
@@ -428,6 +428,7 @@ def bench_slabs(args) -> int:
 
     peak, peak_src = measured_peak_gbs()
     achieved = local_nodes * BYTES_PER_UPDATE / (kms * 1e-3) / 1e9
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -462,7 +463,8 @@ def bench_slabs(args) -> int:
                                          "ms_per_step": alone_ms},
             "checksum_sum_u": float(cs.item()), "checksum_expected": float(args.warmup + args.steps + 1),
         }
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     dist.barrier()
     if runner.transport == "p2p":
         backend.detach_peers()
@@ -470,4 +472,4 @@ def bench_slabs(args) -> int:
     backend.plan.close()
     dist.barrier()
     dist.destroy_process_group()
-    return 0
+    return 0 if emit else line

@@ -548,8 +548,11 @@ int fuse_choice(const tk_plan *p, const tk_run_args *a)
     if (a->n_probes > tk::kFusedMaxProbes) return 0;
     // default: the largest K at which the pass is still HBM-bound on a B200 (FP64 pipe ~60 % busy): the cell
     // recurrences cost 4 FP64 instructions per cell and step without damping, 8 with
-    const int k = std::min<int64_t>(env_int("TK_LAT_FUSE", a->damping == 0.0 ? 48 : 24), a->steps);
-    return k >= 2 ? k : 0;
+    const int kmax = env_int("TK_LAT_FUSE", a->damping == 0.0 ? 48 : 24);
+    if (kmax < 2 || a->steps < 2) return 0;
+    // passes of (nearly) equal length: every pass moves the whole state, so 200 steps are 5 x 40, not 4 x 48 + 8
+    const int64_t npass = (a->steps + kmax - 1) / kmax;
+    return (int)((a->steps + npass - 1) / npass);
 }
 
 int fuse_setup(tk_plan *p, int k)

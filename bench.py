@@ -442,32 +442,38 @@ def main():
         return reference_arm(args, rank)
     if args.workload == "cfg5-ensemble":
         return gpu_ensemble(args)
+    if args.workload == "cfg2-sharded":  # ONE sheet over N GPUs by row bands, one all-reduce per pass
+        from tetrakis_sim_b200.sheet import bench_sheet
+
+        return bench_sheet(args)
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         gpu_single(args)
         return 0
     from tetrakis_sim_b200.slab import bench_slabs  # multi-GPU: layer slabs + halo exchange
 
-    if args.workload is not None and args.workload != "cfg2-2d-8192":
-        return bench_slabs(args)
-    # N > 1, the metric's own configuration: one replica of the sheet per GPU (same workload as N = 1, weak
-    # scaling), followed in the same launch by the layer-slab run of the 3-D lattice that does shard
-    import torch
-    import torch.distributed as dist
+    if args.workload == "cfg2-2d-8192":  # N independent replicas of the 8192^2 sheet, no collective
+        import torch
+        import torch.distributed as dist
 
-    local = int(os.environ.get("LOCAL_RANK", str(rank)))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    line = gpu_single(args, dist=dist, emit=False)
-    slab = None
-    if args.workload is None:
-        slab = bench_slabs(args, emit=False)
-    elif dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        gpu_single(args, dist=dist)
         dist.destroy_process_group()
+        return 0
+    if args.workload is not None:
+        return bench_slabs(args)
+    # N > 1, default: the metric's configuration grown with N -- ONE defect-free sheet held as N row bands, every
+    # GPU holding as many nodes as the single-GPU 8192^2 sheet, one all-reduce of the column sums per pass (weak
+    # scaling) -- followed in the same launch by the layer-slab run of the 3-D lattice with the black hole
+    from tetrakis_sim_b200.sheet import bench_sheet
+
+    line = bench_sheet(args, emit=False, keep_pg=True)
+    slab = bench_slabs(args, emit=False)
     if rank == 0:
-        if slab is not None:
-            line["sharded_3d"] = {k: slab[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "e2e",
-                                                       "gpu_launches", "single_gpu_same_workload",
-                                                       "checksum_sum_u", "checksum_expected")}
+        line["sharded_3d"] = {k: slab[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "e2e",
+                                                   "gpu_launches", "single_gpu_same_workload",
+                                                   "checksum_sum_u", "checksum_expected")}
         print(json.dumps(line), flush=True)
     return 0
 

@@ -155,6 +155,28 @@ int tk_plan_launch_count(const tk_plan *plan, int64_t *launches);
  * largest K at which the pass is still HBM-bound on a B200 rather than bound by the FP64 pipe). */
 int tk_plan_fused_info(tk_plan *plan, int32_t *steps_per_pass, int64_t *fused_steps, int32_t *rows_per_cta,
                        int32_t *ctas_per_sm);
+
+/* ------------------------------------------------------------------------------------------
+ * ONE defect-free sheet sharded over GPUs by rows (one process per GPU).  Rank g holds rows
+ * [row_begin, row_end) of the size x size sheet (node index = ((r - row_begin)*size + c)*4 + q).  Row sums are
+ * local; the column sums and quadrant totals of a band are partial, so between passes they are summed over the
+ * ranks: tk_sheet_pass_local leaves this band's contribution in `exchange` (device memory of
+ * tk_sheet_exchange_doubles() doubles, e.g. a torch tensor), the caller all-reduces it (NCCL, SUM) on the
+ * plan's stream, tk_sheet_pass_commit installs the global sums.  One collective per K steps:
+ *
+ *     tk_sheet_pass_local(plan, 0, coeff, damping, ex); allreduce(ex); tk_sheet_pass_commit(plan, ex);   // sums of u_0, u_{-1}
+ *     repeat: tk_sheet_pass_local(plan, K, coeff, damping, ex); allreduce(ex); tk_sheet_pass_commit(plan, ex);
+ *
+ * State, probes (tk_plan_set_probes / tk_plan_read_probes; row 0 is recorded by the k = 0 call) and the stream
+ * are handled with the generic tk_plan_* calls; tk_plan_run is not available on these plans.
+ * Replaces: physics.py:106-129 on lattice.py:30-73 sheets too large (or too slow) for one GPU. */
+int tk_sheet_band_plan_create(int device, int32_t size, int32_t row_begin, int32_t row_end, tk_plan **out);
+int tk_sheet_exchange_doubles(tk_plan *plan, int64_t *count);
+int tk_sheet_pass_local(tk_plan *plan, int32_t k, double coeff, double damping, void *exchange);
+int tk_sheet_pass_commit(tk_plan *plan, const void *exchange);
+/* Summed CUDA-event time of the pass kernels (lat_fused2d_kernel alone) launched since the previous call, at most
+ * the 64 most recent, and how many they were; synchronises the plan's stream.  For bench.py's roofline. */
+int tk_sheet_kernel_ms(tk_plan *plan, double *total_ms, int64_t *passes);
 int tk_plan_destroy(tk_plan *plan);
 
 /* ------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ ABI_SYMBOLS = (
     "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
     "tk_plan_run", "tk_plan_set_probes", "tk_plan_read_probes", "tk_plan_launch_count", "tk_plan_fused_info", "tk_plan_destroy",
+    "tk_sheet_band_plan_create", "tk_sheet_exchange_doubles", "tk_sheet_pass_local", "tk_sheet_pass_commit", "tk_sheet_kernel_ms",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
     "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
     "tk_lattice_ipc_export", "tk_ipc_open", "tk_ipc_close", "tk_lattice_peer_attach",
@@ -108,6 +109,11 @@ def lib():
     L.tk_plan_read_probes.argtypes = [P, P, POINTER(c_int64)]
     L.tk_plan_launch_count.argtypes = [P, POINTER(c_int64)]
     L.tk_plan_fused_info.argtypes = [P, POINTER(c_int32), POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]
+    L.tk_sheet_band_plan_create.argtypes = [c_int, c_int32, c_int32, c_int32, POINTER(P)]
+    L.tk_sheet_exchange_doubles.argtypes = [P, POINTER(c_int64)]
+    L.tk_sheet_pass_local.argtypes = [P, c_int32, c_double, c_double, c_void_p]
+    L.tk_sheet_pass_commit.argtypes = [P, c_void_p]
+    L.tk_sheet_kernel_ms.argtypes = [P, POINTER(c_double), POINTER(c_int64)]
     L.tk_plan_destroy.argtypes = [P]
     L.tk_lattice_halo_ptrs.argtypes = [P, c_int32, POINTER(P), POINTER(P), POINTER(P), POINTER(P),
                                        POINTER(c_int64)]  # fmt: skip
@@ -220,6 +226,33 @@ class Plan:
         plan = cls(h, "lattice")
         plan.f32 = bool(f32)
         return plan
+
+    @classmethod
+    def sheet_band(cls, size, row_begin, row_end, device: int = 0) -> "Plan":
+        """Rows [row_begin, row_end) of ONE defect-free sheet sharded over GPUs (tk_sheet_band_plan_create)."""
+        h = c_void_p()
+        check(lib().tk_sheet_band_plan_create(device, int(size), int(row_begin), int(row_end), ctypes.byref(h)))
+        return cls(h, "sheet_band")
+
+    @property
+    def exchange_doubles(self) -> int:
+        n = c_int64(0)
+        check(lib().tk_sheet_exchange_doubles(self._h, ctypes.byref(n)))
+        return n.value
+
+    def pass_local(self, k: int, coeff: float, damping: float, exchange_ptr: int):
+        """k steps on this band (k = 0: only the sums of both time levels); leaves the band's column sums and
+        quadrant totals in the device buffer at ``exchange_ptr`` for the caller's all-reduce."""
+        check(lib().tk_sheet_pass_local(self._h, int(k), float(coeff), float(damping), c_void_p(exchange_ptr)))
+
+    def pass_commit(self, exchange_ptr: int):
+        check(lib().tk_sheet_pass_commit(self._h, c_void_p(exchange_ptr)))
+
+    def sheet_kernel_ms(self):
+        """(summed device time of the pass kernels since the last call, number of passes)."""
+        ms, n = c_double(0.0), c_int64(0)
+        check(lib().tk_sheet_kernel_ms(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     # -- lifetime -----------------------------------------------------------------------------
     def close(self):

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) lat_zero_sums_kernel(int S, double *__res
 // finalised row sums: totpart[lvl][blk][q].  Only needed when a run enters the fused mode; afterwards
 // lat_finalise2_kernel produces them as a by-product.
 __global__ void __launch_bounds__(256)
-lat_totparts_kernel(int S, int nblk, const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
+lat_totparts_kernel(int nrows, int nblk, const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
                     double *__restrict__ totpart)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,7 +72,7 @@ lat_totparts_kernel(int S, int nblk, const double *__restrict__ rowinfo, const d
     const int q = t & 3, blk = (t >> 2) % nblk, lvl = (t >> 2) / nblk;
     const double *src = lvl ? rowinfo_prev : rowinfo;
     double a = 0.0;
-    for (int r = blk * 8; r < min(S, blk * 8 + 8); ++r) a += src[(size_t)r * 8 + q];
+    for (int r = blk * 8; r < min(nrows, blk * 8 + 8); ++r) a += src[(size_t)r * 8 + q];
     totpart[((size_t)lvl * nblk + blk) * 4 + q] = a;
 }
 
@@ -81,7 +81,7 @@ lat_totparts_kernel(int S, int nblk, const double *__restrict__ rowinfo, const d
 // plus the per-block quadrant totals the next lat_tables_kernel starts from.
 // grid = 2 * (nrowblk + ncolblk); first half = state a (u_{t+K}), second half = state b (u_{t+K-1}).
 __global__ void __launch_bounds__(256)
-lat_finalise2_kernel(int S, int nsegk, int nchunk, int nrowblk, int ncolblk, const double *__restrict__ prow_a,
+lat_finalise2_kernel(int S, int nrows, int nsegk, int nchunk, int nrowblk, int ncolblk, const double *__restrict__ prow_a,
                      const double *__restrict__ pcol_a, const double *__restrict__ prow_b,
                      const double *__restrict__ pcol_b, double *__restrict__ rowinfo_a, double *__restrict__ colinfo_a,
                      double *__restrict__ rowinfo_b, double *__restrict__ colinfo_b, double *__restrict__ totpart)
@@ -96,7 +96,7 @@ lat_finalise2_kernel(int S, int nsegk, int nchunk, int nrowblk, int ncolblk, con
     if (blk < nrowblk) {
         const int line = blk * 8 + w;
         double acc = 0.0;
-        if (line < S) {
+        if (line < nrows) {
             const double *p = prow + (size_t)line * nsegk * 4;
             const int len = nsegk * 4;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -146,20 +146,61 @@ lat_finalise2_kernel(int S, int nsegk, int nchunk, int nrowblk, int ncolblk, con
     }
 }
 
+// Row-band plans (one sheet sharded over GPUs by rows): the column sums and quadrant totals of a band are
+// partial; they travel in one exchange buffer that the host all-reduces between passes.
+//   ex[0 .. 4S)      column sums of the current state      ex[4S .. 8S)      of the previous state
+//   ex[8S .. 8S+4)   quadrant totals of the current state  ex[8S+4 .. 8S+8)  of the previous state
+__global__ void __launch_bounds__(256)
+sheet_pack_kernel(int S, int nblk, const double *__restrict__ colinfo, const double *__restrict__ colinfo_prev,
+                  const double *__restrict__ totpart, double *__restrict__ ex)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 8 * S) {
+        const int lvl = t >= 4 * S, j = t - lvl * 4 * S;
+        ex[t] = (lvl ? colinfo_prev : colinfo)[(size_t)(j >> 2) * 8 + (j & 3)];
+    } else if (t < 8 * S + 8) {
+        const int j = t - 8 * S, lvl = j >> 2, q = j & 3;
+        double a = 0.0;
+        for (int blk = 0; blk < nblk; ++blk) a += totpart[((size_t)lvl * nblk + blk) * 4 + q];
+        ex[t] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sheet_unpack_kernel(int S, const double *__restrict__ ex, double *__restrict__ colinfo,
+                    double *__restrict__ colinfo_prev, double *__restrict__ tot_global)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 8 * S) {
+        const int lvl = t >= 4 * S, j = t - lvl * 4 * S;
+        (lvl ? colinfo_prev : colinfo)[(size_t)(j >> 2) * 8 + (j & 3)] = ex[t];
+    } else if (t < 8 * S + 8) {
+        tot_global[t - 8 * S] = ex[t];
+    }
+}
+
 // One thread per row or column line.  Advances the line's four quadrant sums X_k (k = 0..K-1) with the
 // recurrences above and, alongside, the response y of a cell at rest to the forcing coeff * X_k:
 //   y_{k+1} = ca y_k + cb y_{k-1} + coeff sum_q y_k + coeff X_k,   y_0 = y_{-1} = 0.
 // resp[line][k][q] = y_{k+1}[q]; the pass adds y_K to u_{t+K} and y_{K-1} to u_{t+K-1} (and y_{k+1}
 // to a probe's value at step t+k+1).
 __global__ void __launch_bounds__(128)
-lat_tables_kernel(int S, int K, double coeff, double damping, double ca, double cb,
+lat_tables_kernel(int S, int nrows, int K, double coeff, double damping, double ca, double cb,
                   const double *__restrict__ rowinfo, const double *__restrict__ rowinfo_prev,
                   const double *__restrict__ colinfo, const double *__restrict__ colinfo_prev,
-                  const double *__restrict__ totpart, int nblk, double *__restrict__ respR, double *__restrict__ respC)
+                  const double *__restrict__ totpart, int nblk, const double *__restrict__ tot_global,
+                  double *__restrict__ respR, double *__restrict__ respC)
 {
     // quadrant totals of both time levels: every CTA sums the per-block totals in the same fixed order
+    // (row-band plans of a sheet sharded over GPUs pass the all-reduced totals in tot_global instead)
     __shared__ double red[2][128];
-    {
+    if (tot_global != nullptr) {
+        if (threadIdx.x < 4) {
+            red[0][threadIdx.x] = tot_global[threadIdx.x];
+            red[1][threadIdx.x] = tot_global[4 + threadIdx.x];
+        }
+        __syncthreads();
+    } else {
         const int t = threadIdx.x, q = t & 3;
         double a = 0.0, b = 0.0;
         for (int blk = t >> 2; blk < nblk; blk += 32) {
@@ -178,9 +219,9 @@ lat_tables_kernel(int S, int K, double coeff, double damping, double ca, double 
         }
     }
     const int line = blockIdx.x * blockDim.x + threadIdx.x;
-    if (line >= 2 * S) return;
-    const bool is_col = line >= S;
-    const int idx = is_col ? line - S : line;
+    if (line >= nrows + S) return;
+    const bool is_col = line >= nrows;
+    const int idx = is_col ? line - nrows : line;
     const double *src = (is_col ? colinfo : rowinfo) + (size_t)idx * 8;
     const double *srcp = (is_col ? colinfo_prev : rowinfo_prev) + (size_t)idx * 8;
     double *dst = (is_col ? respC : respR) + (size_t)idx * K * 4;
@@ -219,7 +260,7 @@ lat_tables_kernel(int S, int K, double coeff, double damping, double ca, double 
 //   ua: in u_t,     out u_{t+K}      ub: in u_{t-1}, out u_{t+K-1}
 template <int MINB, bool UNDAMPED>
 __global__ void __launch_bounds__(256, MINB)
-lat_fused2d_kernel(int S, int K, double *__restrict__ ua, double *__restrict__ ub, const double *__restrict__ respR,
+lat_fused2d_kernel(int S, int nrows, int K, double *__restrict__ ua, double *__restrict__ ub, const double *__restrict__ respR,
                    const double *__restrict__ respC, double *__restrict__ prow_a, double *__restrict__ pcol_a,
                    double *__restrict__ prow_b, double *__restrict__ pcol_b, double ca, double cb, double coeff,
                    int rchunk, int nchunk, int nsegk, int nct, int pf_rows,
@@ -235,7 +276,7 @@ lat_fused2d_kernel(int S, int K, double *__restrict__ ua, double *__restrict__ u
     const int ct = blockIdx.x % nct;
     const int ch = blockIdx.x / nct;
     const int r_begin = ch * rchunk;
-    const int r_end = min(S, r_begin + rchunk);
+    const int r_end = min(nrows, r_begin + rchunk);
     const int col0 = ct * ncol;
     // j = 0..3: y_K[q] (added to u_{t+K}); j = 4..7: y_{K-1}[q] (added to u_{t+K-1}; zero when K = 1)
     for (int i = threadIdx.x; i < ncol * 8; i += blockDim.x) {

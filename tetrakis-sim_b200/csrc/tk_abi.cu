@@ -78,7 +78,7 @@ int dev_upload(T **p, const std::vector<T> &v)
     return TK_OK;
 }
 
-enum PlanKind { kGraph = 1, kLattice = 2 };
+enum PlanKind { kGraph = 1, kLattice = 2, kSheetBand = 3 };
 
 constexpr size_t kHistoryChunkBytes = (size_t)1 << 30;
 
@@ -144,6 +144,12 @@ struct tk_plan {
     // which finalised sums are current (plain 2-D sheets only; lets a run skip the sums-only passes)
     bool sums_cur_valid = false;             // rowinfo/colinfo hold the sums of buf[cur]
     int sums_prev = 0;                       // rowinfo_prev/colinfo_prev: 0 unknown, 1 valid, 2 buf[cur^1] is all zero
+    // rows this plan holds: S for a whole sheet, fewer for one row band of a sheet sharded over GPUs
+    // (kSheetBand: column sums and totals are partial and travel through an all-reduced exchange buffer)
+    int nrows = 0, row_begin = 0;
+    double *ftot_global = nullptr;           // kSheetBand: all-reduced quadrant totals, 2 levels
+    std::vector<cudaEvent_t> band_ev;        // kSheetBand: ring of event pairs around the pass kernels
+    long long band_ev_next = 0, band_ev_read = 0;
     int fuse_wc = 8, fuse_rchunk = 0, fuse_nchunk = 0, fuse_nsegk = 0, fuse_occ = 0;
     double *tabR = nullptr, *tabC = nullptr, *rowinfo_prev = nullptr, *colinfo_prev = nullptr;
     double *prow_b = nullptr, *fpcol_a = nullptr, *fpcol_b = nullptr, *ftot = nullptr;
@@ -559,7 +565,7 @@ int fuse_setup(tk_plan *p, int k)
 {
     if (p->fuse_k >= k) return TK_OK;  // tables are sized for the largest K seen; shorter passes reuse them
     k = std::max(k, 64);               // (cudaMalloc is slow: do not grow them run by run)
-    const int S = p->lat.S;
+    const int S = p->lat.S, R = p->nrows;
     int mb = env_int("TK_LAT_FUSE_MINB", 4);
     if (mb < 2 || mb > 4) mb = 3;
     const int nseg32 = (S + 31) / 32;
@@ -572,12 +578,12 @@ int fuse_setup(tk_plan *p, int k)
     const long long slots = (long long)p->sm_count * occ;
     int best = 16;
     double best_eff = -1.0;
-    if ((long long)((S + 15) / 16) * nct < slots) {
+    if ((long long)((R + 15) / 16) * nct < slots) {
         const long long want = std::max<long long>(1, slots / std::max(1, nct));
-        best = (int)std::max<long long>(4, std::min<long long>((S + want - 1) / want, 16));
+        best = (int)std::max<long long>(4, std::min<long long>((R + want - 1) / want, 16));
     } else {
-        for (int rc_ = 16; rc_ <= rc_cap && rc_ <= std::max(16, S); ++rc_) {
-            const long long tiles = (long long)((S + rc_ - 1) / rc_) * nct;
+        for (int rc_ = 16; rc_ <= rc_cap && rc_ <= std::max(16, R); ++rc_) {
+            const long long tiles = (long long)((R + rc_ - 1) / rc_) * nct;
             const long long waves = (tiles + slots - 1) / slots;
             const double eff = (double)tiles / (double)(waves * slots) * (1.0 / (1.0 + 2.0 / rc_));
             if (eff > best_eff + 1e-9) { best_eff = eff; best = rc_; }
@@ -585,14 +591,14 @@ int fuse_setup(tk_plan *p, int k)
     }
     int rchunk = env_int("TK_LAT_FUSE_RCHUNK", best);
     if (rchunk < 1 || rchunk > rc_cap) rchunk = best;
-    const int nchunk = (S + rchunk - 1) / rchunk;
-    TK_CHK(plan_alloc(p, &p->tabR, (size_t)S * k * 4, true));
+    const int nchunk = (R + rchunk - 1) / rchunk;
+    TK_CHK(plan_alloc(p, &p->tabR, (size_t)R * k * 4, true));
     TK_CHK(plan_alloc(p, &p->tabC, (size_t)S * k * 4, true));
     if (!p->rowinfo_prev) {
-        TK_CHK(plan_alloc(p, &p->rowinfo_prev, (size_t)S * 8, true));
+        TK_CHK(plan_alloc(p, &p->rowinfo_prev, (size_t)R * 8, true));
         TK_CHK(plan_alloc(p, &p->colinfo_prev, (size_t)S * 8, true));
-        TK_CHK(plan_alloc(p, &p->prow_b, (size_t)S * nseg32 * 4, true));
-        TK_CHK(plan_alloc(p, &p->ftot, (size_t)2 * ((S + 7) / 8) * 4, true));  // per-block quadrant totals, 2 levels
+        TK_CHK(plan_alloc(p, &p->prow_b, (size_t)R * nseg32 * 4, true));
+        TK_CHK(plan_alloc(p, &p->ftot, (size_t)2 * ((R + 7) / 8) * 4, true));  // per-block quadrant totals, 2 levels
         TK_CHK(plan_alloc(p, &p->fpcol_a, (size_t)nchunk * S * 4, true));
         TK_CHK(plan_alloc(p, &p->fpcol_b, (size_t)nchunk * S * 4, true));
         p->fuse_minb = mb; p->fuse_wc = wc; p->fuse_rchunk = rchunk; p->fuse_nchunk = nchunk;
@@ -617,9 +623,9 @@ int fuse_prepare(tk_plan *p)
         TK_CHK(lat_finalise_sums(p, p->prow, p->pcol, p->nsegk, p->nchunk, p->rowinfo_prev, p->colinfo_prev));
     }
     p->sums_prev = 1;
-    const int nblk = (p->lat.S + 7) / 8;
+    const int nblk = (p->nrows + 7) / 8;
     tk::lat_totparts_kernel<<<(unsigned)((2 * nblk * 4 + 255) / 256), 256, 0, p->stream>>>(
-        p->lat.S, nblk, p->rowinfo, p->rowinfo_prev, p->ftot);
+        p->nrows, nblk, p->rowinfo, p->rowinfo_prev, p->ftot);
     p->launches++;
     TK_CUDA(cudaGetLastError());
     return TK_OK;
@@ -638,16 +644,18 @@ int fuse_pass(tk_plan *p, int k, cudaEvent_t ev_begin, cudaEvent_t ev_end)
     }
     const double g = p->damping;
     const double ca = (2.0 - g) - p->coeff * (2.0 * S + 4.0), cb = -(1.0 - g);
-    const int nrowblk = (S + 7) / 8, ncolblk = (S * 4 + 31) / 32;
-    tk::lat_tables_kernel<<<(unsigned)((2 * S + 127) / 128), 128, 0, p->stream>>>(
-        S, k, p->coeff, g, ca, cb, p->rowinfo, p->rowinfo_prev, p->colinfo, p->colinfo_prev, p->ftot, nrowblk, p->tabR,
-        p->tabC);
+    const int R = p->nrows;
+    const int nrowblk = (R + 7) / 8, ncolblk = (S * 4 + 31) / 32;
+    if (k > 0)
+        tk::lat_tables_kernel<<<(unsigned)((R + S + 127) / 128), 128, 0, p->stream>>>(
+            S, R, k, p->coeff, g, ca, cb, p->rowinfo, p->rowinfo_prev, p->colinfo, p->colinfo_prev, p->ftot, nrowblk,
+            p->kind == kSheetBand ? p->ftot_global : nullptr, p->tabR, p->tabC);
     const unsigned grid = (unsigned)(p->fuse_nchunk * nct);
     const size_t sm = fuse_smem(wc, p->fuse_rchunk);
     if (ev_begin) TK_CUDA(cudaEventRecord(ev_begin, p->stream));
 #define TK_FUSE_LAUNCH1(MB, UD)                                                                                 \
     tk::lat_fused2d_kernel<MB, UD><<<grid, wc * 32, sm, p->stream>>>(                                           \
-        S, k, p->buf[p->cur], p->buf[p->cur ^ 1], p->tabR, p->tabC, p->prow, p->fpcol_a, p->prow_b, p->fpcol_b, ca, cb, \
+        S, R, k, p->buf[p->cur], p->buf[p->cur ^ 1], p->tabR, p->tabC, p->prow, p->fpcol_a, p->prow_b, p->fpcol_b, ca, cb, \
         p->coeff, p->fuse_rchunk, p->fuse_nchunk, p->fuse_nsegk, nct, p->pf_rows, pr, p->probe_series,          \
         p->ctr_mode ? p->ctr_dev : nullptr, p->probe_row)
 #define TK_FUSE_LAUNCH(MB)              \
@@ -662,7 +670,7 @@ int fuse_pass(tk_plan *p, int k, cudaEvent_t ev_begin, cudaEvent_t ev_end)
 #undef TK_FUSE_LAUNCH1
     if (ev_end) TK_CUDA(cudaEventRecord(ev_end, p->stream));
     tk::lat_finalise2_kernel<<<(unsigned)(2 * (nrowblk + ncolblk)), 256, 0, p->stream>>>(
-        S, p->fuse_nsegk, p->fuse_nchunk, nrowblk, ncolblk, p->prow, p->fpcol_a, p->prow_b, p->fpcol_b, p->rowinfo,
+        S, R, p->fuse_nsegk, p->fuse_nchunk, nrowblk, ncolblk, p->prow, p->fpcol_a, p->prow_b, p->fpcol_b, p->rowinfo,
         p->colinfo, p->rowinfo_prev, p->colinfo_prev, p->ftot);
     p->launches += 3;
     TK_CUDA(cudaGetLastError());
@@ -1042,6 +1050,7 @@ int tk_lattice_plan_create_ex(int device, const tk_lattice_desc *d, uint32_t fla
         p->wc = 1;
     }
     p->plain2d = halo == 0 && Lloc == 1 && ndet == 0 && corr.empty() && p->esz == 8;
+    p->nrows = (int)S;
     if (p->esz == 8 && !p->wz3d && env_int("TK_LAT_BULK", 0)) {  // TMA-staged variant of the default shapes
         p->bulk_stages = env_int("TK_LAT_BULK_STAGES", halo ? 3 : 4);
         if (p->bulk_stages != 2 && p->bulk_stages != 3 && p->bulk_stages != 4 && p->bulk_stages != 6)
@@ -1367,6 +1376,7 @@ int tk_lattice_step_end(tk_plan *p)
 int tk_plan_run(tk_plan *p, const tk_run_args *a)
 {
     TK_REQUIRE(p && a, "NULL argument");
+    TK_REQUIRE(p->kind != kSheetBand, "row-band plans are stepped with tk_sheet_pass_local / tk_sheet_pass_commit");
     TK_REQUIRE(a->steps >= 0, "steps must be >= 0");
     TK_REQUIRE(a->n_probes == 0 || (a->probe_index && a->probe_out), "probe arrays NULL");
     TK_CUDA(cudaSetDevice(p->device));
@@ -1803,6 +1813,119 @@ int tk_plan_fused_info(tk_plan *p, int32_t *steps_per_pass, int64_t *fused_steps
     return TK_OK;
 }
 
+// ------------------------------------------------------------------ one sheet sharded over GPUs by rows
+#define TK_BAND_TRY(x)     \
+    do {                   \
+        rc = (x);          \
+        if (rc) {          \
+            tk_plan_destroy(p); \
+            return rc;     \
+        }                  \
+    } while (0)
+int tk_sheet_band_plan_create(int device, int32_t size, int32_t row_begin, int32_t row_end, tk_plan **out)
+{
+    TK_REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    TK_REQUIRE(size >= 1 && 0 <= row_begin && row_begin < row_end && row_end <= size,
+               "row band [%d,%d) not inside [0,%d)", row_begin, row_end, size);
+    int rc = check_device(device);
+    if (rc) return rc;
+    tk_plan *p = new tk_plan();
+    p->kind = kSheetBand;
+    p->esz = 8;
+    const long long S = size, R = row_end - row_begin;
+    p->n = R * S * 4;
+    p->alloc = p->n;
+    p->state_off = 0;
+    p->nrows = (int)R;
+    p->row_begin = row_begin;
+    p->lat.S = size;
+    p->lat.Lloc = 1;
+    p->max_degree = 2 * S + 1;  // lattice.py:30-73 without defects: 3 in the cell + 2 (S-1) in the row and column cliques
+    p->pf_rows = env_int("TK_LAT_PREFETCH", 1);
+    TK_BAND_TRY(plan_common_init(p, device));
+    TK_BAND_TRY(plan_alloc(p, &p->buf[0], (size_t)p->alloc, true));
+    TK_BAND_TRY(plan_alloc(p, &p->buf[1], (size_t)p->alloc, true));
+    TK_BAND_TRY(plan_alloc(p, &p->rowinfo, (size_t)R * 8, true));
+    TK_BAND_TRY(plan_alloc(p, &p->colinfo, (size_t)S * 8, true));
+    TK_BAND_TRY(plan_alloc(p, &p->prow, (size_t)R * ((S + 31) / 32) * 4, true));
+    TK_BAND_TRY(plan_alloc(p, &p->ftot_global, 8, true));
+    TK_BAND_TRY(fuse_setup(p, 64));  // response tables, previous-level sums, partial buffers, tiling
+    *out = p;
+    return TK_OK;
+}
+
+#undef TK_BAND_TRY
+
+int tk_sheet_exchange_doubles(tk_plan *p, int64_t *count)
+{
+    TK_REQUIRE(p && p->kind == kSheetBand && count, "not a row-band plan");
+    *count = 8LL * p->lat.S + 8;
+    return TK_OK;
+}
+
+int tk_sheet_pass_local(tk_plan *p, int32_t k, double coeff, double damping, void *exchange)
+{
+    TK_REQUIRE(p && p->kind == kSheetBand && exchange, "not a row-band plan / NULL exchange buffer");
+    TK_REQUIRE(k >= 0, "k must be >= 0");
+    TK_CUDA(cudaSetDevice(p->device));
+    p->coeff = coeff;
+    p->damping = damping;
+    int rc = fuse_setup(p, k);
+    if (rc) return rc;
+    if (k == 0) {  // start of a run: probes' row 0; the pass below only produces the sums of both levels
+        if (double *row = next_probe_row(p)) {
+            tk::gather_kernel<<<(p->n_probes + 127) / 128, 128, 0, p->stream>>>(p->buf[p->cur], p->probe_idx, row,
+                                                                              p->n_probes, nullptr);
+            p->launches++;
+        }
+    }
+    if (p->band_ev.empty()) {
+        p->band_ev.resize(128, nullptr);
+        for (auto &e : p->band_ev) TK_CUDA(cudaEventCreate(&e));
+    }
+    const size_t slot = (size_t)(p->band_ev_next % 64) * 2;
+    rc = fuse_pass(p, k, p->band_ev[slot], p->band_ev[slot + 1]);
+    if (rc) return rc;
+    p->band_ev_next++;
+    const int S = p->lat.S;
+    tk::sheet_pack_kernel<<<(unsigned)((8 * S + 8 + 255) / 256), 256, 0, p->stream>>>(
+        S, (p->nrows + 7) / 8, p->colinfo, p->colinfo_prev, p->ftot, static_cast<double *>(exchange));
+    p->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_sheet_kernel_ms(tk_plan *p, double *total_ms, int64_t *passes)
+{
+    TK_REQUIRE(p && p->kind == kSheetBand && total_ms && passes, "not a row-band plan / NULL argument");
+    TK_CUDA(cudaSetDevice(p->device));
+    TK_CUDA(cudaStreamSynchronize(p->stream));
+    const long long first = std::max(p->band_ev_read, p->band_ev_next - 64);
+    double sum = 0.0;
+    for (long long i = first; i < p->band_ev_next; ++i) {
+        float ms = 0.f;
+        TK_CUDA(cudaEventElapsedTime(&ms, p->band_ev[(size_t)(i % 64) * 2], p->band_ev[(size_t)(i % 64) * 2 + 1]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *passes = p->band_ev_next - first;
+    p->band_ev_read = p->band_ev_next;
+    return TK_OK;
+}
+
+int tk_sheet_pass_commit(tk_plan *p, const void *exchange)
+{
+    TK_REQUIRE(p && p->kind == kSheetBand && exchange, "not a row-band plan / NULL exchange buffer");
+    TK_CUDA(cudaSetDevice(p->device));
+    const int S = p->lat.S;
+    tk::sheet_unpack_kernel<<<(unsigned)((8 * S + 8 + 255) / 256), 256, 0, p->stream>>>(
+        S, static_cast<const double *>(exchange), p->colinfo, p->colinfo_prev, p->ftot_global);
+    p->launches++;
+    TK_CUDA(cudaGetLastError());
+    return TK_OK;
+}
+
 int tk_plan_set_probes(tk_plan *p, int64_t n_probes, const int64_t *probe_index, int64_t rows)
 {
     TK_REQUIRE(p, "plan is NULL");
@@ -1841,6 +1964,8 @@ int tk_plan_destroy(tk_plan *p)
     if (p->pen) cudaFree(p->pen);
     if (p->energy_series) cudaFree(p->energy_series);
     if (p->ctr_dev) cudaFree(p->ctr_dev);
+    for (cudaEvent_t e : p->band_ev)
+        if (e) cudaEventDestroy(e);
     if (p->own_stream && p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return TK_OK;

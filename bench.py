@@ -438,6 +438,9 @@ def main():
 
         faulthandler.dump_traceback_later(int(os.environ["TK_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output (it goes to stdout when NCCL_DEBUG is
+    # set in the environment) is sent to stderr instead
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         return reference_arm(args, rank)
     if args.workload == "cfg5-ensemble":
@@ -478,5 +481,36 @@ def main():
     return 0
 
 
+def _main_with_clean_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write there too (NCCL prints its version banner to
+    stdout on communicator creation): run with file descriptor 1 pointing at stderr and give the JSON line, which
+    the arms print through ``print``, the real stdout at the end."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    captured = []
+    import builtins
+
+    orig_print = builtins.print
+
+    def json_print(*a, **k):
+        if len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{") and k.get("file") is None:
+            captured.append(a[0])
+        else:
+            orig_print(*a, **k)
+
+    builtins.print = json_print
+    try:
+        rc = main()
+    finally:
+        builtins.print = orig_print
+        sys.stdout.flush()
+        os.dup2(real, 1)
+        os.close(real)
+    for line in captured:
+        print(line, flush=True)
+    return rc
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_main_with_clean_stdout())

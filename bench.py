@@ -3,14 +3,22 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
-One "step" = one fused leapfrog pass over the whole lattice (every node updated once).
+One "step" = one leapfrog update of every node of the lattice.
 Workloads (config.workload):
-  cfg2-2d-8192      BASELINE configs[1]: 2-D tetrakis 8192x8192, no defect, fp64   (default at N=1)
+  cfg2-2d-8192      BASELINE configs[1]: 2-D tetrakis 8192x8192, no defect, fp64   (default at N=1).  The sheet
+                    has no defect, so tk_plan_run advances it in K-step passes (kernels_fused.cuh, 32/K bytes
+                    per update); TK_LAT_FUSE=0 measures the step-by-step kernel (24 bytes per update) instead.
+                    At N>1 with this name: N independent replicas.
+  cfg2-sharded      the same sheet grown with N (size 8192*sqrt(N)) and held as N row bands, one all-reduce of
+                    the column sums per pass; --size fixes the sheet (strong scaling)    (default at N>1, with
+                    the cfg3 slab run of the same launch reported under "sharded_3d")
   cfg3-slab-1024x64 BASELINE configs[2] shape: 3-D 1024x1024, 64 layers PER GPU, black hole r=64 at the
-                    global centre, layer slabs + halo exchange over NCCL            (default at N>1)
+                    global centre, layer slabs + halo push over NVLink peer memory (or NCCL)
+  cfg4-3d-512       BASELINE configs[3]: 3-D 512^3 singularity, mass 2000, pruned edges
+  cfg5-ensemble     BASELINE configs[4]: 65 536 independent 13x13x7 simulations
 Prints ONE JSON line (rank 0).  `value` is device-timed with the state resident in HBM; `e2e` is the same
 metric through the C ABI with host buffers (kicks H2D, probe series + final state D2H inside the timed
-region); `roofline` is the step kernel's algorithmic bytes / its CUDA-event time against the measured HBM
+region); `roofline` is the dominant kernel's algorithmic bytes / its CUDA-event time against the measured HBM
 peak; `cpu_baseline` is the oracle (oracle/wave_oracle.c, OpenMP) on this box's host cores.
 `--impl reference` times that CPU restatement alone (the reference itself is pure Python over networkx and
 cannot even build these lattices: 2.2e12 edges for cfg2 -- BASELINE.md section 1).
@@ -184,7 +192,7 @@ def cpu_run(workload: str, steps: int, warmup: int, budget_s: float):
 def reference_arm(args, rank):
     if rank != 0:
         return 0
-    workload = args.workload or ("cfg2-2d-8192" if args.gpus == 1 else "cfg3-slab-1024x64")
+    workload = args.workload or ("cfg2-2d-8192" if args.gpus == 1 else "cfg2-sharded")
     res = cpu_run(workload, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,

@@ -139,3 +139,23 @@ def test_fused_long_run_stays_within_the_parity_bar():
     assert rel_inf(hist.probe_series, ref["probes"]) < 1e-10
     freq, spectrum, _ = tk.run_fft(hist, kick)
     assert wo.folded_bin(spectrum) == wo.folded_bin(wo.run_fft(ref["probes"][:, 0], hist.dt)[1])
+
+
+def test_full_size_config_2_sheet_against_the_oracle():
+    """BASELINE configs[1] at its full size (8192^2 = 268 M nodes): two fused passes of 48 steps against the C
+    oracle stepping one step at a time, all 268 M final values and the probe series."""
+    S, steps = 8192, 96
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.bench_kick_node()
+    far = spec.node(spec.index(kick) + 4 * 1000 * S + 4 * 777 + 1)
+    hist = _run(spec, steps, {kick: 1.0}, 0.0, [kick, far], dt=0.1)
+    assert hist.metadata["stability_adjusted"] and hist.fused == {**hist.fused, "steps_per_pass": 48, "fused_steps": 96}
+    n = spec.num_slots
+    u0 = np.zeros(n)
+    u0[spec.index(kick)] = 1.0
+    ref = wo.run_structured(S, 1, None, None, None, [], u0, steps, (1.0 * hist.dt) ** 2, 0.0,
+                            probes=[spec.index(kick), spec.index(far)])
+    assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
+    scale = np.max(np.abs(ref["u"]))
+    assert np.max(np.abs(hist.final_state - ref["u"])) < 1e-12 * scale
+    assert abs(hist.final_state.sum() - (1.0 + steps)) < 1e-8  # sum_i u_t(i) = 1 + t

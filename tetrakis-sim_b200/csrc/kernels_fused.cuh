@@ -182,7 +182,7 @@ sheet_unpack_kernel(int S, const double *__restrict__ ex, double *__restrict__ c
 // One thread per row or column line.  Advances the line's four quadrant sums X_k (k = 0..K-1) with the
 // recurrences above and, alongside, the response y of a cell at rest to the forcing coeff * X_k:
 //   y_{k+1} = ca y_k + cb y_{k-1} + coeff sum_q y_k + coeff X_k,   y_0 = y_{-1} = 0.
-// resp[line][k][q] = y_{k+1}[q]; the pass adds y_K to u_{t+K} and y_{K-1} to u_{t+K-1} (and y_{k+1}
+// resp[k][line][q] = y_{k+1}[q]; the pass adds y_K to u_{t+K} and y_{K-1} to u_{t+K-1} (and y_{k+1}
 // to a probe's value at step t+k+1).
 __global__ void __launch_bounds__(128)
 lat_tables_kernel(int S, int nrows, int K, double coeff, double damping, double ca, double cb,
@@ -224,7 +224,9 @@ lat_tables_kernel(int S, int nrows, int K, double coeff, double damping, double 
     const int idx = is_col ? line - nrows : line;
     const double *src = (is_col ? colinfo : rowinfo) + (size_t)idx * 8;
     const double *srcp = (is_col ? colinfo_prev : rowinfo_prev) + (size_t)idx * 8;
-    double *dst = (is_col ? respC : respR) + (size_t)idx * K * 4;
+    // layout [k][line][q]: the threads of a warp (consecutive lines) store contiguously
+    const size_t nlines = is_col ? (size_t)S : (size_t)nrows;
+    double *dst = (is_col ? respC : respR) + (size_t)idx * 4;
     double X[4], Xp[4], T[4], Tp[4], y[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -243,7 +245,7 @@ lat_tables_kernel(int S, int nrows, int K, double coeff, double damping, double 
             const double yn = fma(ca, y[q], fma(cb, yp[q], yc)) + coeff * X[q];
             yp[q] = y[q];
             y[q] = yn;
-            dst[k * 4 + q] = yn;
+            dst[(size_t)k * nlines * 4 + q] = yn;
             const double xn = 2.0 * X[q] - Xp[q] + coeff * ((XT + T[q]) - s4 * X[q]) - damping * (X[q] - Xp[q]);
             const double tn = 2.0 * T[q] - Tp[q] + coeff * (TT - 4.0 * T[q]) - damping * (T[q] - Tp[q]);
             Xp[q] = X[q];
@@ -282,12 +284,12 @@ lat_fused2d_kernel(int S, int nrows, int K, double *__restrict__ ua, double *__r
     for (int i = threadIdx.x; i < ncol * 8; i += blockDim.x) {
         const int cl_ = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
         const int c = col0 + cl_;
-        const double v = (c < S && k >= 0) ? respC[((size_t)c * K + k) * 4 + q] : 0.0;
+        const double v = (c < S && k >= 0) ? respC[((size_t)k * S + c) * 4 + q] : 0.0;
         colresp[((size_t)(j >> 1) * ncol + cl_) * 2 + (j & 1)] = v;
     }
     for (int i = threadIdx.x; i < (r_end - r_begin) * 8; i += blockDim.x) {
         const int rl = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
-        rowresp[i] = k >= 0 ? respR[((size_t)(r_begin + rl) * K + k) * 4 + q] : 0.0;
+        rowresp[i] = k >= 0 ? respR[((size_t)k * nrows + r_begin + rl) * 4 + q] : 0.0;
     }
     __syncthreads();
 
@@ -354,7 +356,7 @@ lat_fused2d_kernel(int S, int nrows, int K, double *__restrict__ ua, double *__r
                             const int pq = probes.q[p];
                             const double dq = pq == 0 ? d0 : (pq == 1 ? d1 : (pq == 2 ? d2 : -((d0 + d1) + d2)));
                             probe_series[(size_t)(base_row + k) * probes.n + p] =
-                                (m + dq) + (respR[((size_t)r * K + k) * 4 + pq] + respC[((size_t)c0 * K + k) * 4 + pq]);
+                                (m + dq) + (respR[((size_t)k * nrows + r) * 4 + pq] + respC[((size_t)k * S + c0) * 4 + pq]);
                         }
                 }
             }

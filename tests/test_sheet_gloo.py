@@ -72,6 +72,7 @@ def test_band_ownership_and_pass_lengths():
             assert max(e - b for b, e in bands) - min(e - b for b, e in bands) <= 1
     assert pass_lengths(200, 48) == [40] * 5
     assert pass_lengths(203, 8) == [8] * 25 + [3]
-    assert pass_lengths(33, 16) == [11] * 3
+    assert pass_lengths(33, 16) == [16, 16, 1]
+    assert pass_lengths(100, 48) == [40, 40, 20]
     assert pass_lengths(1, 48) == [1] and pass_lengths(0, 48) == []
     assert all(sum(pass_lengths(s, k)) == s for s in range(1, 60) for k in (1, 2, 7, 48))

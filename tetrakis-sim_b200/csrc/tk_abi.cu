@@ -558,7 +558,11 @@ int fuse_choice(const tk_plan *p, const tk_run_args *a)
     if (kmax < 2 || a->steps < 2) return 0;
     // passes of (nearly) equal length: every pass moves the whole state, so 200 steps are 5 x 40, not 4 x 48 + 8
     const int64_t npass = (a->steps + kmax - 1) / kmax;
-    return (int)((a->steps + npass - 1) / npass);
+    int64_t k = (a->steps + npass - 1) / npass;
+    // the pass kernel's step loop is unrolled by 8 and its remainder is slow (K = 54 costs what K = 64 does):
+    // round the pass length up to a multiple of 8 where K allows
+    if (k > 8 && (k + 7) / 8 * 8 <= kmax) k = (k + 7) / 8 * 8;
+    return (int)std::min<int64_t>(k, a->steps);
 }
 
 int fuse_setup(tk_plan *p, int k)

@@ -16,6 +16,7 @@ Workloads (config.workload):
                     global centre, layer slabs + halo push over NVLink peer memory (or NCCL)
   cfg4-3d-512       BASELINE configs[3]: 3-D 512^3 singularity, mass 2000, pruned edges
   cfg5-ensemble     BASELINE configs[4]: 65 536 independent 13x13x7 simulations
+  ell-tetrakis-64x16 / ell-grid-256   the generic sliced-ELL graph kernel on an explicit CSR (44 + 4w bytes/update)
 Prints ONE JSON line (rank 0).  `value` is device-timed with the state resident in HBM; `e2e` is the same
 metric through the C ABI with host buffers (kicks H2D, probe series + final state D2H inside the timed
 region); `roofline` is the dominant kernel's algorithmic bytes / its CUDA-event time against the measured HBM
@@ -354,6 +355,116 @@ def gpu_single(args, dist=None, emit=True):
     return line
 
 
+def _csr_tetrakis(S, L):
+    """Adjacency-ordered CSR of a defect-free 3-D tetrakis lattice built with NumPy (no networkx): node
+    (z, r, c, q) -> ((z*S + r)*S + c)*4 + q; neighbours = cell mates, row mates, column mates, z-1, z+1."""
+    n = L * S * S * 4
+    idx = np.arange(n, dtype=np.int64)
+    q, cell = idx & 3, idx >> 2
+    c, r, z = cell % S, (cell // S) % S, cell // (S * S)
+    cols = []
+    for dq in (1, 2, 3):
+        cols.append((cell << 2) + ((q + dq) & 3))
+    for d in range(1, S):
+        cols.append(((((z * S + r) * S + (c + d) % S)) << 2) + q)
+    for d in range(1, S):
+        cols.append(((((z * S + (r + d) % S) * S + c)) << 2) + q)
+    nb = np.stack(cols, axis=1)
+    width = nb.shape[1]
+    zm = np.where(z > 0, idx - S * S * 4, -1)
+    zp = np.where(z < L - 1, idx + S * S * 4, -1)
+    nb = np.concatenate([nb, zm[:, None], zp[:, None]], axis=1)
+    keep = nb >= 0
+    deg = keep.sum(1)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    return rowptr, nb[keep].astype(np.int32), deg.astype(np.float64), width + 2
+
+
+def _csr_grid(m):
+    """7-point grid graph on m^3 nodes (non-periodic)."""
+    n = m ** 3
+    idx = np.arange(n, dtype=np.int64)
+    x, y, z = idx % m, (idx // m) % m, idx // (m * m)
+    nb = np.stack([np.where(x > 0, idx - 1, -1), np.where(x < m - 1, idx + 1, -1),
+                   np.where(y > 0, idx - m, -1), np.where(y < m - 1, idx + m, -1),
+                   np.where(z > 0, idx - m * m, -1), np.where(z < m - 1, idx + m * m, -1)], axis=1)
+    keep = nb >= 0
+    deg = keep.sum(1)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    return rowptr, nb[keep].astype(np.int32), deg.astype(np.float64), 6
+
+
+def gpu_ell(args):
+    """--workload ell-tetrakis-64x16 | ell-grid-256: the generic sliced-ELL graph kernel (what any networkx
+    graph runs on) on a synthetic CSR.  Algorithmic bytes per update = 44 + 4*w: u, u_prev, u_next,
+    degree, inv_mass, potential + one 4-byte index per padded neighbour slot; the gathered u is cache traffic."""
+    import torch
+
+    import tetrakis_sim_b200 as tk
+
+    torch.cuda.init()
+    if args.workload == "ell-grid-256":
+        m = args.size or 256
+        rowptr, colidx, deg, w = _csr_grid(m)
+        desc = f"7-point grid graph {m}^3, sliced ELL width 6"
+    else:
+        S, L = args.size or 64, args.layers or 16
+        rowptr, colidx, deg, w = _csr_tetrakis(S, L)
+        desc = f"3-D tetrakis {S}x{S}x{L} as an explicit graph (degree {int(deg.max())}), sliced ELL"
+    n = len(deg)
+    t0 = time.perf_counter()
+    plan = tk.Plan.graph(rowptr, colidx, deg, np.ones(n), np.zeros(n), device=0)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    coeff = 1.0 / float(deg.max())
+    kidx = [n // 2]
+    clk = ClockSampler(0).start()
+    plan.set_state_sparse(kidx, [1.0])
+    plan.run(args.warmup, coeff, 0.0, probes=kidx)
+    torch.cuda.synchronize()
+    l0 = plan.launches
+    with clk:
+        out = plan.run(args.steps, coeff, 0.0, probes=kidx, timed=True, kernel_timing=True)
+        torch.cuda.synchronize()
+    launches = plan.launches - l0
+    ms, kms = out["elapsed_ms"], out["step_kernel_ms"]
+    bpu = 44.0 + 4.0 * w
+    peak, peak_src = measured_peak_gbs()
+    achieved = n * bpu * args.steps / (kms * 1e-3) / 1e9
+    final_t, final = pinned_empty(n)
+    from tetrakis_sim_b200 import _lib
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan.set_state_sparse(kidx, [1.0])
+    o2 = plan.run(args.steps, coeff, 0.0, probes=kidx)
+    _lib.check(_lib.lib().tk_plan_get_state(plan._h, _lib._p(final), None))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    checksum = float(final.sum())
+    plan.close()
+    line = {
+        "metric": METRIC, "value": n * args.steps / (ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "graph": desc, "nodes": n, "edges_directed": int(rowptr[-1]),
+                   "plan_build_s": t_build, "l2": f"index array {4 * w * n / 1e9:.2f} GB"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "graph_step_kernel",
+                     "bytes_per_update": bpu, "algorithmic_bytes_per_launch": n * bpu,
+                     "kernel_ms_per_launch": kms / args.steps, "kernel_share_of_step": kms / ms},
+        "cpu_baseline": None,
+        "e2e": {"value": n * args.steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": 16.0 / args.steps,
+                "d2h_bytes_per_step": (final.nbytes + o2["probes"].nbytes) / args.steps, "seconds": e2e_s},
+        "gpu_launches": launches, "clocks": clk.summary(),
+        "checksum_sum_u": checksum, "checksum_expected": float(args.steps + 1),
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def gpu_ensemble(args):
     """--workload cfg5-ensemble: BASELINE configs[4], 65 536 independent 13x13x7 simulations over a
     radius x damping x dt grid, 50 steps each; simulations are block-distributed over the ranks, no
@@ -453,6 +564,8 @@ def main():
         return reference_arm(args, rank)
     if args.workload == "cfg5-ensemble":
         return gpu_ensemble(args)
+    if args.workload in ("ell-tetrakis-64x16", "ell-grid-256"):
+        return gpu_ell(args)
     if args.workload == "cfg2-sharded":  # ONE sheet over N GPUs by row bands, one all-reduce per pass
         from tetrakis_sim_b200.sheet import bench_sheet
 

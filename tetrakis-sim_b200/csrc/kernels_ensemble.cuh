@@ -30,6 +30,23 @@ struct EnsDev {
 
 constexpr int kEnsMaxCorr = 32;
 
+// Line pair i of the row/column-sum phase: i < nline/2 rows, else columns; pair = (z, x, p) -> lines (z, x, 2p),
+// (z, x, 2p+1).  off/stride address the pair's first cell and the walk along the line (in doubles), dst is the
+// index in rs (columns: nline + index, cs is laid out right behind rs), m0/m1 the participation masks.
+__device__ __forceinline__ void line_pair(int i, int S, int nline, const unsigned long long *lmask, int &off,
+                                          int &stride, int &dst, unsigned long long &m0, unsigned long long &m1)
+{
+    const bool is_col = i >= nline / 2;
+    const int lp = is_col ? i - nline / 2 : i;
+    const int pr = lp & 1, x = (lp >> 1) % S, z = (lp >> 1) / S;
+    const int l0 = ((z * S + x) * 4) + 2 * pr;
+    off = (is_col ? (z * S * S + x) * 4 : (z * S + x) * S * 4) + 2 * pr;
+    stride = is_col ? S * 4 : 4;
+    dst = (is_col ? nline : 0) + l0;
+    m0 = lmask[(is_col ? nline : 0) + l0];
+    m1 = lmask[(is_col ? nline : 0) + l0 + 1];
+}
+
 // Shared-memory layout (per CTA = per simulation in flight):
 //   ua, ub        [N]        the two state buffers (u_{t+1} overwrites u_{t-1})
 //   rs, cs        [nline]    masked row / column sums of u_t
@@ -52,9 +69,11 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
     double *tws = twc + nt;
     double *csig = tws + nt;                                                       // [kEnsMaxCorr]
     unsigned long long *lmask = reinterpret_cast<unsigned long long *>(csig + kEnsMaxCorr);  // [2*nline]
-    uint4 *meta = reinterpret_cast<uint4 *>(
-        (reinterpret_cast<uintptr_t>(lmask + 2 * nline) + 15) & ~(uintptr_t)15);  // [ncell], 16 B aligned
-    int *ca = reinterpret_cast<int *>(meta + ncell);                               // [kEnsMaxCorr]
+    // (byte offsets from the start of shared memory: pointer arithmetic that keeps the shared address space)
+    const size_t meta_off = ((size_t)(reinterpret_cast<unsigned char *>(lmask + 2 * nline) - tk_smem) + 15) & ~(size_t)15;
+    uint4 *meta = reinterpret_cast<uint4 *>(tk_smem + meta_off);                   // [ncell], 16 B aligned
+    double *tabA = reinterpret_cast<double *>(meta + ncell);                       // [256]: u coefficient by degree
+    int *ca = reinterpret_cast<int *>(tabA + 256);                                 // [kEnsMaxCorr]
     int *cb = ca + kEnsMaxCorr;
     unsigned char *bits = reinterpret_cast<unsigned char *>(cb + kEnsMaxCorr);      // [ncell]
 
@@ -124,30 +143,47 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
                     if (ca[k] == cell * 4 + q) dg += (int)csig[k];
                 deg4 |= (unsigned)(dg & 0xFF) << (8 * q);
             }
-            meta[cell] = make_uint4(deg4, (unsigned)rl | ((unsigned)cl << 16),
-                                    (f & 0xFFu) | ((fm & 0xFu) << 8) | ((fp & 0xFu) << 12), 0u);
-        }
-        double *u = ua, *w = ub;
-        const int plane = S * S * 4;
-        for (int t = 0; t < P.steps; ++t) {
-            __syncthreads();
-            // phase A: masked row / column sums of u_t
-            for (int i = tid; i < 2 * nline; i += nth) {
-                const bool is_col = i >= nline;
-                const int l = is_col ? i - nline : i;
-                const int q = l & 3, x = (l >> 2) % S, z = (l >> 2) / S;
-                const double *p = u + (is_col ? (z * S * S + x) * 4 : (z * S + x) * S * 4) + q;
-                const int stride = is_col ? S * 4 : 4;
-                unsigned long long m = lmask[i];
-                double a0 = 0.0, a1 = 0.0;
-                int k = 0;
-                for (; k + 1 < S; k += 2) {
-                    if (m & 1ull) a0 += p[k * stride];
-                    if (m & 2ull) a1 += p[(k + 1) * stride];
-                    m >>= 2;
+            // bit h of .w: half h (quadrants 2h, 2h+1) is ORDINARY -- both nodes alive and participating, unit
+            // mass, no potential, no edge correction -- and takes the short update path
+            unsigned fast = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                bool ok = ((f >> (2 * h)) & 3u) == 3u && ((f >> (4 + 2 * h)) & 3u) == 3u;
+                for (int j = 0; j < 2 && ok; ++j) {
+                    const int node = cell * 4 + 2 * h + j;
+                    if (has_attr && (gim[node] != 1.0 || gv[node] != 0.0)) ok = false;
+                    for (int k = 0; k < ncorr; ++k)
+                        if (ca[k] == node) ok = false;
                 }
-                if (k < S && (m & 1ull)) a0 += p[k * stride];
-                (is_col ? cs : rs)[l] = a0 + a1;
+                fast |= (unsigned)ok << h;
+            }
+            meta[cell] = make_uint4(deg4, (unsigned)rl | ((unsigned)cl << 16),
+                                    (f & 0xFFu) | ((fm & 0xFu) << 8) | ((fp & 0xFu) << 12), fast);
+        }
+        // ordinary node of degree d:  u+ = tabA[d] u + (damping - 1) u- + coeff (cell + row + col + z-1 + z+1)
+        for (int d = tid; d < 256; d += nth) tabA[d] = (2.0 - damping) - coeff * (3.0 + (double)d);
+        const int plane = S * S * 4;
+        const double cbm = damping - 1.0;
+        for (int t = 0; t < P.steps; ++t) {
+            double *const u = (t & 1) ? ub : ua;  // u_t
+            double *const w = (t & 1) ? ua : ub;  // u_{t-1}, overwritten by u_{t+1}
+            __syncthreads();
+            // phase A: masked row / column sums of u_t; one thread per line PAIR (quadrants 2p, 2p+1 of a row or
+            // column sit in one 16-byte slot of every cell: LDS.128)
+            for (int i = tid; i < nline; i += nth) {
+                int off, stride, dst;
+                unsigned long long m0, m1;
+                line_pair(i, S, nline, lmask, off, stride, dst, m0, m1);
+                const double *p = u + off;
+                double a0 = 0.0, a1 = 0.0;
+                for (int k = 0; k < S; ++k) {
+                    const double2 v = *reinterpret_cast<const double2 *>(p + k * stride);
+                    if (m0 & 1ull) a0 += v.x;
+                    if (m1 & 1ull) a1 += v.y;
+                    m0 >>= 1;
+                    m1 >>= 1;
+                }
+                *reinterpret_cast<double2 *>(rs + dst) = make_double2(a0, a1);  // cs follows rs: dst >= nline is a column
             }
             __syncthreads();
             // phase B: update; u_{t+1} overwrites u_{t-1}.  One lane per HALF cell (2 quadrants, one
@@ -168,40 +204,47 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
                 double2 m0 = make_double2(0.0, 0.0), p0 = m0;
                 if (f & 0xF00u) m0 = *reinterpret_cast<const double2 *>(u + n0 - plane);
                 if (f & 0xF000u) p0 = *reinterpret_cast<const double2 *>(u + n0 + plane);
-                const double uq[2] = {a.x, a.y}, up[2] = {wa.x, wa.y};
-                const double RS[2] = {r0.x, r0.y}, CS[2] = {k0.x, k0.y};
-                const double zm[2] = {m0.x, m0.y}, zp[2] = {p0.x, p0.y};
-                double mine = 0.0;
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    if ((f >> (2 * h + j)) & 1u) mine += uq[j];
+                const unsigned fh = f >> (2 * h);  // bit 0 / 1: part of this lane's nodes; 8,9: z-1; 12,13: z+1
+                const double mine = ((fh & 1u) ? a.x : 0.0) + ((fh & 2u) ? a.y : 0.0);
                 const double other = __shfl_xor_sync(__activemask(), mine, 1);
                 const double cellsum = h ? other + mine : mine + other;  // same order in both lanes
                 double un[2];
+                if ((md.w >> h) & 1u) {
+                    // ordinary half cell: no masks on the node itself, coefficients from the degree table
+                    const unsigned dg = md.x >> (16 * h);
+                    const double s0 = (((cellsum + r0.x) + k0.x) + ((fh & 0x100u) ? m0.x : 0.0)) + ((fh & 0x1000u) ? p0.x : 0.0);
+                    const double s1 = (((cellsum + r0.y) + k0.y) + ((fh & 0x200u) ? m0.y : 0.0)) + ((fh & 0x2000u) ? p0.y : 0.0);
+                    un[0] = fma(tabA[dg & 0xFFu], a.x, fma(cbm, wa.x, coeff * s0));
+                    un[1] = fma(tabA[(dg >> 8) & 0xFFu], a.y, fma(cbm, wa.y, coeff * s1));
+                    if ((unsigned)(kick - n0) < 2u) series[t + 1] = kick == n0 ? un[0] : un[1];
+                } else {
+                    const double uq[2] = {a.x, a.y}, up[2] = {wa.x, wa.y};
+                    const double RS[2] = {r0.x, r0.y}, CS[2] = {k0.x, k0.y};
+                    const double zm[2] = {m0.x, m0.y}, zp[2] = {p0.x, p0.y};
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int q = 2 * h + j, node = n0 + j;
-                    const bool part = (f >> q) & 1u, alive = (f >> (4 + q)) & 1u;
-                    double lap = 0.0;
-                    if (part) {
-                        double nsum = (cellsum - uq[j]) + (RS[j] - uq[j]) + (CS[j] - uq[j]);
-                        if ((f >> (8 + q)) & 1u) nsum += zm[j];
-                        if ((f >> (12 + q)) & 1u) nsum += zp[j];
-                        lap = nsum;
+                    for (int j = 0; j < 2; ++j) {
+                        const int q = 2 * h + j, node = n0 + j;
+                        const bool part = (f >> q) & 1u, alive = (f >> (4 + q)) & 1u;
+                        double lap = 0.0;
+                        if (part) {
+                            double nsum = (cellsum - uq[j]) + (RS[j] - uq[j]) + (CS[j] - uq[j]);
+                            if ((f >> (8 + q)) & 1u) nsum += zm[j];
+                            if ((f >> (12 + q)) & 1u) nsum += zp[j];
+                            lap = nsum;
+                        }
+                        for (int k = 0; k < ncorr; ++k)
+                            if (ca[k] == node) lap += csig[k] * u[cb[k]];
+                        lap -= (double)((md.x >> (8 * q)) & 0xFFu) * uq[j];  // degree incl. corrections
+                        double im = 1.0, v = 0.0;
+                        if (has_attr) { im = gim[node]; v = gv[node]; }
+                        const double rnew = 2.0 * uq[j] - up[j] + (coeff * im) * lap - (coeff * v) * uq[j] -
+                                            damping * (uq[j] - up[j]);
+                        un[j] = alive ? rnew : 0.0;
+                        if (node == kick) series[t + 1] = un[j];
                     }
-                    for (int k = 0; k < ncorr; ++k)
-                        if (ca[k] == node) lap += csig[k] * u[cb[k]];
-                    lap -= (double)((md.x >> (8 * q)) & 0xFFu) * uq[j];  // degree incl. corrections
-                    double im = 1.0, v = 0.0;
-                    if (has_attr) { im = gim[node]; v = gv[node]; }
-                    const double rnew = 2.0 * uq[j] - up[j] + (coeff * im) * lap - (coeff * v) * uq[j] -
-                                        damping * (uq[j] - up[j]);
-                    un[j] = alive ? rnew : 0.0;
-                    if (node == kick) series[t + 1] = un[j];
                 }
                 *reinterpret_cast<double2 *>(w + n0) = make_double2(un[0], un[1]);
             }
-            double *tmp = u; u = w; w = tmp;
         }
         __syncthreads();
         // epilogue: probe series out, |DFT| (reference physics.py:162-163) and argmax (batch.py:205)
@@ -243,7 +286,7 @@ inline size_t ensemble_smem_bytes(int S, int L, int steps)
     const size_t ncell = (size_t)L * S * S, N = ncell * 4, nline = (size_t)L * S * 4, nt = steps + 1;
     size_t b = (2 * N + 2 * nline + 3 * nt + kEnsMaxCorr) * sizeof(double);  // ua ub rs cs series twc tws csig
     b += 2 * nline * sizeof(unsigned long long);                             // lmask
-    b += ncell * sizeof(uint4);                                              // meta
+    b += ncell * sizeof(uint4) + 256 * sizeof(double);                       // meta, tabA
     b += 2 * kEnsMaxCorr * sizeof(int) + ncell + 16;                         // ca cb bits + alignment slack
     return (b + 15) & ~(size_t)15;
 }

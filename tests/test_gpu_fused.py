@@ -162,3 +162,22 @@ def test_full_size_config_2_sheet_against_the_oracle():
     scale = np.max(np.abs(ref["u"]))
     assert np.max(np.abs(hist.final_state - ref["u"])) < 1e-12 * scale
     assert abs(hist.final_state.sum() - (1.0 + steps)) < 1e-8  # sum_i u_t(i) = 1 + t
+
+
+def test_fused_passes_record_eight_probes_sharing_cells_rows_and_warps():
+    """Probes in one cell (all four quadrants), the same node twice, neighbours in one warp segment, first and
+    last row: the pass records each from the lane that owns its cell."""
+    S, steps = 100, 53
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.kick_node()
+    ki = spec.index(kick)
+    cell = ki - ki % 4
+    pidx = [cell, cell + 1, cell + 2, cell + 3, cell + 1, cell + 4, 2, spec.num_slots - 3]
+    probes = [spec.node(i) for i in pidx]
+    hist = _run(spec, steps, {kick: 1.0, spec.node(cell + 6): 0.5}, 0.01, probes)
+    assert hist.fused["steps_per_pass"] == 24 and hist.fused["fused_steps"] == steps
+    u0 = np.zeros(spec.num_slots)
+    u0[ki], u0[cell + 6] = 1.0, 0.5
+    ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, 0.01, pidx)
+    assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
+    assert rel_inf(hist.final_state, ref["u"]) < 1e-12

@@ -19,7 +19,7 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".inc"))]
     out.append(os.path.join(os.path.dirname(HERE), "include", "tetrakis_b200.h"))
     return out
 

@@ -38,7 +38,7 @@ def pass_lengths(steps: int, kmax: int) -> list[int]:
         return []
     npass = -(-steps // max(kmax, 1))
     k = -(-steps // npass)
-    if k > 8 and -(-k // 8) * 8 <= kmax:  # the pass kernel's step loop is unrolled by 8 (tk_abi.cu:fuse_choice)
+    if k > 8 and -(-k // 8) * 8 <= kmax:  # the pass kernel's step loop is unrolled by 8 (csrc/host_fused.inc:fuse_choice)
         k = -(-k // 8) * 8
     k = min(k, steps)
     out = [k] * (steps // k)

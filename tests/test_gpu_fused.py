@@ -119,7 +119,7 @@ def test_fusion_is_not_used_where_the_recurrences_do_not_close(monkeypatch):
     sheet = tk.LatticeSpec(size=40, dim=2)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
-        full = tk.run_wave_sim(sheet, steps=32, dt=0.05, record="all")
+        full = tk.run_wave_sim(sheet, steps=32, dt=0.05, record="all")  # every state: nothing to fuse
         en = tk.run_wave_sim(tk.LatticeSpec(size=256, dim=2), steps=32, dt=0.05, energy=True)
     assert full.fused["steps_per_pass"] == 0 and en.fused["steps_per_pass"] == 0
     assert _run(sheet, 32, None, 0.0, None).fused["steps_per_pass"] == 8
@@ -181,3 +181,26 @@ def test_fused_passes_record_eight_probes_sharing_cells_rows_and_warps():
     ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, 0.01, pidx)
     assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
     assert rel_inf(hist.final_state, ref["u"]) < 1e-12
+
+
+@pytest.mark.parametrize("stride,steps", [(16, 100), (96, 200), (7, 30), (53, 120)])
+def test_snapshots_every_k_steps_ride_on_fused_passes(stride, steps):
+    """record="all" with snapshot_every=s: passes whose length divides s; a prime s larger than K falls back."""
+    S = 90
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.kick_node()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        hist = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, c=1.0, dt=0.05, record="all",
+                               snapshot_every=stride, probes=[kick])
+    want = {16: 16, 96: 48, 7: 7, 53: 0}[stride]
+    assert hist.fused["steps_per_pass"] == want
+    u0 = np.zeros(spec.num_slots)
+    u0[spec.index(kick)] = 1.0
+    n = spec.num_slots
+    full = wo.run_structured_numpy(S, 1, np.full(n, 3, np.uint8), np.ones(n), np.zeros(n), [], u0, steps,
+                                   (1.0 * hist.dt) ** 2, 0.0)
+    assert hist.array.shape == (steps // stride + 1, n)
+    assert rel_inf(hist.array, full[::stride]) < 1e-12
+    assert rel_inf(hist.probe_series[:, 0], full[:, spec.index(kick)]) < 1e-12
+    assert rel_inf(hist.final_state, full[-1]) < 1e-12

@@ -318,7 +318,11 @@ def gpu_single(args, dist=None, emit=True):
     if fk:
         tiling = {"steps_per_pass": fk, "cells_per_lane": 1, "segs_per_cta": tiling["segs_per_cta"],
                   "rows_per_cta": fused["rows_per_cta"], "ctas_per_sm": fused["ctas_per_sm"],
-                  "single_steps": nsingle}
+                  "single_steps": nsingle,
+                  "temporal_blocking": (f"{npass} passes of <= {fk} steps: every node update is computed (cell-local, in "
+                                        "registers), the intermediate states are not stored; the row/column sums of the "
+                                        "intermediate steps follow from closed recurrences because the sheet has no "
+                                        "defect.  TK_LAT_FUSE=0 runs one step per launch (24 B per update).")}
     plan.close()
 
     cpu = None

@@ -151,8 +151,9 @@ int tk_plan_launch_count(const tk_plan *plan, int64_t *launches);
  * Reports how the LAST tk_plan_run went: steps per pass (0 = step by step), how many of its steps ran in
  * fused passes (steps mod K >= 2 runs as one shorter pass, a single left-over step as an ordinary step),
  * rows per CTA and resident CTAs per SM of the pass kernel.
- * Environment: TK_LAT_FUSE = 0 (off) or the steps per pass, >= 2 (default 48 without damping, 24 with: the
- * largest K at which the pass is still HBM-bound on a B200 rather than bound by the FP64 pipe). */
+ * Environment: TK_LAT_FUSE = 0 (off) or the steps per pass, >= 2.  Default: the largest K at which the pass is
+ * still bound by moving the state (or by its launches) rather than by the FP64 pipe of a B200 -- 48 without
+ * damping and 24 with on sheets that do not fit L2, up to 1024 on small ones. */
 int tk_plan_fused_info(tk_plan *plan, int32_t *steps_per_pass, int64_t *fused_steps, int32_t *rows_per_cta,
                        int32_t *ctas_per_sm);
 

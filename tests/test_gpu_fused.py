@@ -22,6 +22,15 @@ def _oracle(S, u0, up0, steps, coeff, damping, probes):
                              probes=probes, uprev0=None if up0 is None else up0.copy())
 
 
+def _default_kmax(S, damping):
+    """Mirror of csrc/host_fused.inc:fuse_choice: longer passes on sheets that are launch-bound."""
+    ncell = float(S) * S
+    t_fp = ncell * (1.0 if damping == 0.0 else 2.0) * 16.4e-6 / 6.7e7
+    t_pass = ncell * 128.0 / 6.3e12 + 40e-6
+    k = int(0.6 * t_pass / t_fp)
+    return max(48 if damping == 0.0 else 24, min(k, 1024)) // 8 * 8
+
+
 def _expected(steps, kmax):
     """(steps per pass, steps covered by passes): passes of nearly equal length, a single left-over step runs
     as an ordinary step."""
@@ -93,7 +102,7 @@ def test_fused_passes_continue_from_a_dense_state_with_a_previous_level():
     try:
         plan.set_state(u0, up0)
         out = plan.run(steps, coeff, 0.01, probes=[3, 1000])
-        assert (plan.fused["steps_per_pass"], plan.fused["fused_steps"]) == _expected(41, 24) == (24, 41)
+        assert (plan.fused["steps_per_pass"], plan.fused["fused_steps"]) == _expected(41, _default_kmax(S, 0.01)) == (41, 41)
         got = plan.get_state()
         out2 = plan.run(16, coeff, 0.01, probes=[3])  # a second call continues the same simulation
         got2 = plan.get_state()
@@ -134,7 +143,7 @@ def test_fused_long_run_stays_within_the_parity_bar():
     spec = tk.LatticeSpec(size=S, dim=2)
     kick = spec.kick_node()
     hist = _run(spec, steps, {kick: 1.0}, 0.0, [kick], dt=0.1)
-    assert hist.metadata["stability_adjusted"] and hist.fused["steps_per_pass"] == _expected(steps, 48)[0]
+    assert hist.metadata["stability_adjusted"] and hist.fused["steps_per_pass"] == _expected(steps, _default_kmax(S, 0.0))[0] == 1000
     u0 = np.zeros(spec.num_slots)
     u0[spec.index(kick)] = 1.0
     ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, 0.0, [spec.index(kick)])
@@ -175,7 +184,7 @@ def test_fused_passes_record_eight_probes_sharing_cells_rows_and_warps():
     pidx = [cell, cell + 1, cell + 2, cell + 3, cell + 1, cell + 4, 2, spec.num_slots - 3]
     probes = [spec.node(i) for i in pidx]
     hist = _run(spec, steps, {kick: 1.0, spec.node(cell + 6): 0.5}, 0.01, probes)
-    assert hist.fused["steps_per_pass"] == 24 and hist.fused["fused_steps"] == steps
+    assert (hist.fused["steps_per_pass"], hist.fused["fused_steps"]) == _expected(steps, _default_kmax(S, 0.01)) == (53, 53)
     u0 = np.zeros(spec.num_slots)
     u0[ki], u0[cell + 6] = 1.0, 0.5
     ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, 0.01, pidx)
@@ -184,8 +193,9 @@ def test_fused_passes_record_eight_probes_sharing_cells_rows_and_warps():
 
 
 @pytest.mark.parametrize("stride,steps", [(16, 100), (96, 200), (7, 30), (53, 120)])
-def test_snapshots_every_k_steps_ride_on_fused_passes(stride, steps):
+def test_snapshots_every_k_steps_ride_on_fused_passes(stride, steps, monkeypatch):
     """record="all" with snapshot_every=s: passes whose length divides s; a prime s larger than K falls back."""
+    monkeypatch.setenv("TK_LAT_FUSE", "48")
     S = 90
     spec = tk.LatticeSpec(size=S, dim=2)
     kick = spec.kick_node()

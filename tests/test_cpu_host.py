@@ -281,3 +281,22 @@ def test_fused_pass_algebra_matches_the_oracle():
         up = up + yR[K - 2][:, None, :] + yC[K - 2][None, :, :]
     assert np.abs(u.ravel() - ref["u"]).max() <= 1e-13 * np.abs(ref["u"]).max()
     assert np.abs(up.ravel() - ref["uprev"]).max() <= 1e-13 * np.abs(ref["u"]).max()
+
+
+def test_bench_csr_builders_match_the_lattice_graph():
+    """bench.py builds explicit CSR graphs with NumPy for the sliced-ELL workloads: same adjacency as the
+    LatticeSpec graph (which is checked against the reference's build_sheet elsewhere)."""
+    import bench
+
+    S, L = 6, 3
+    rowptr, colidx, deg, width = bench._csr_tetrakis(S, L)
+    spec = tk.LatticeSpec(size=S, dim=3, layers=L)
+    G = spec.to_networkx()
+    assert len(deg) == spec.num_slots and width == 3 + 2 * (S - 1) + 2
+    for i in range(0, spec.num_slots, 7):
+        want = {spec.index(m) for m in G[spec.node(i)]}
+        got = set(colidx[rowptr[i]:rowptr[i + 1]].tolist())
+        assert got == want and deg[i] == len(want)
+    rowptr, colidx, deg, width = bench._csr_grid(4)
+    assert len(deg) == 64 and width == 6 and rowptr[-1] == 2 * 3 * 4 * 4 * 3  # 3 * m^2 * (m-1) edges, both directions
+    assert deg.min() == 3 and deg.max() == 6

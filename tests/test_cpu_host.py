@@ -300,3 +300,75 @@ def test_bench_csr_builders_match_the_lattice_graph():
     rowptr, colidx, deg, width = bench._csr_grid(4)
     assert len(deg) == 64 and width == 6 and rowptr[-1] == 2 * 3 * 4 * 4 * 3  # 3 * m^2 * (m-1) edges, both directions
     assert deg.min() == 3 and deg.max() == 6
+
+
+@pytest.mark.parametrize("kw", [dict(defect="blackhole", radius=3.3),
+                                dict(defect="singularity", radius=2.5, mass=50.0, potential=2.0),
+                                dict(defect="singularity", radius=2.0, mass=2000.0, prune_edges=True),
+                                dict(defect="wedge")])
+def test_fused_pass_with_defects_algebra_matches_the_oracle(kw):
+    """Groundwork for K-step passes on sheets WITH defects (open item 1), restated in NumPy:
+    rows R_d and columns C_d that touch a special cell form a "cross" that is stepped one step at a time together
+    with all line sums -- for a line outside the cross the sum splits into a bulk part B with the closed recurrence
+        B+ = ca B + cb B- + coeff (sum_q B + n_bulk * LineSum + sum of the crossing lines' sums over the bulk)
+    and a cross part summed from the cross cells -- and the bulk then takes one cell-local K-step pass driven by
+    the recorded sums.  Checked against the oracle's step-by-step run for every defect kind."""
+    from oracle import wave_oracle as wo
+
+    S, steps, K, g = 32, 40, 8, 0.01
+    coeff = 0.9 / (2 * S + 1)
+    spec = tk.LatticeSpec(size=S, dim=2, **kw)
+    n = spec.num_slots
+    flags, im, pot = np.full(n, 3, np.uint8), np.ones(n), np.zeros(n)
+    si, sf, sm, sv = spec.specials()
+    flags[si], im[si], pot[si] = sf, sm, sv
+    corr = spec.corrections()
+    u0 = np.zeros(n)
+    kick = spec.index(spec.kick_node())
+    u0[kick], u0[(kick + 4 * S * 5 + 13) % n] = 1.0, -0.3
+    u0[(flags & 1) == 0] = 0.0
+    ref = wo.run_structured(S, 1, flags, im, pot, corr, u0, steps, coeff, g)
+
+    P = ((flags >> 1) & 1).reshape(S, S, 4).astype(float)
+    A = (flags & 1).reshape(S, S, 4).astype(float)
+    IM, V = im.reshape(S, S, 4), pot.reshape(S, S, 4)
+    special = (P.min(2) < 1) | (A.min(2) < 1) | (IM.min(2) != 1) | (IM.max(2) != 1) | (np.abs(V).max(2) > 0)
+    for a_, b_, _ in corr:
+        special[(a_ // 4) // S, (a_ // 4) % S] = special[(b_ // 4) // S, (b_ // 4) % S] = True
+    Rd, Cd = special.any(1), special.any(0)
+    cross = (Rd[:, None] | Cd[None, :])[:, :, None]
+    n_bulk_cols, n_bulk_rows = (~Cd).sum(), (~Rd).sum()
+    deg = (P * ((P.sum(2, keepdims=True) - 1) + (P.sum(1, keepdims=True) - 1) + (P.sum(0, keepdims=True) - 1))).reshape(-1)
+    for a_, _, s_ in corr:
+        deg[a_] += s_
+    deg = deg.reshape(S, S, 4)
+    ca, cb = (2 - g) - coeff * (2 * S + 4), -(1 - g)
+
+    def step_general(u, up, RS, CS):  # the reference update with masks, tags and edge corrections
+        cell = (P * u).sum(2, keepdims=True)
+        lap = (P * ((cell - u) + (RS[:, None, :] - u) + (CS[None, :, :] - u)) - deg * u).reshape(-1)
+        for a_, b_, s_ in corr:
+            lap[a_] += s_ * u.reshape(-1)[b_]
+        return (2 * u - up + coeff * IM * lap.reshape(S, S, 4) - coeff * V * u - g * (u - up)) * A
+
+    u, up = u0.reshape(S, S, 4).copy(), np.zeros((S, S, 4))
+    for _ in range(steps // K):
+        B, Bp = (u * ~cross).sum(1), (up * ~cross).sum(1)  # bulk parts of the row sums (zero for rows in R_d)
+        D, Dp = (u * ~cross).sum(0), (up * ~cross).sum(0)
+        uc, upc, tabR, tabC = u.copy(), up.copy(), [], []
+        for _k in range(K):  # the cross and every line sum, one step at a time
+            RS = B + (P * uc * cross).sum(1)
+            CS = D + (P * uc * cross).sum(0)
+            tabR.append(RS)
+            tabC.append(CS)
+            un = step_general(uc, upc, RS, CS)
+            Bn = ca * B + cb * Bp + coeff * (B.sum(1, keepdims=True) + n_bulk_cols * RS + CS[~Cd].sum(0)[None, :])
+            Dn = ca * D + cb * Dp + coeff * (D.sum(1, keepdims=True) + n_bulk_rows * CS + RS[~Rd].sum(0)[None, :])
+            Bn[Rd], Dn[Cd] = 0.0, 0.0
+            Bp, B, Dp, D = B, Bn, D, Dn
+            upc, uc = np.where(cross, uc, upc), np.where(cross, un, uc)
+        ub, upb = u.copy(), up.copy()
+        for k in range(K):  # the bulk: cell-local, driven by the recorded sums
+            ub, upb = ca * ub + cb * upb + coeff * (ub.sum(2, keepdims=True) + tabR[k][:, None, :] + tabC[k][None, :, :]), ub
+        u, up = np.where(cross, uc, ub), np.where(cross, upc, upb)
+    assert np.abs(u.reshape(-1) - ref["u"]).max() <= 1e-13 * np.abs(ref["u"]).max()

@@ -18,6 +18,12 @@
  *   lattice plans : linear index ((z*size + r)*size + c)*4 + q, q = 0..3 for "ABCD"; the
  *                   reference's (r,c[,z],q) tuples (lattice.py:30,48-54) map onto it.  A plan that
  *                   owns the slab [z_begin, z_end) uses LOCAL indices with z relative to z_begin.
+ *   row-band plans: one defect-free sheet sharded over GPUs (tk_sheet_*): ((r - row_begin)*size + c)*4 + q.
+ *
+ * Families of entry points: plans (tk_graph_plan_create, tk_lattice_plan_create[_ex], tk_sheet_band_plan_create),
+ * state and probes (tk_plan_set_state*, tk_plan_get_state, tk_plan_set_probes, tk_plan_read_probes), stepping
+ * (tk_plan_run; tk_lattice_step_* + halo/peer/flag calls for 3-D slabs across GPUs; tk_sheet_pass_* for row bands),
+ * spectra (tk_dft_abs), ensembles (tk_ensemble_run), introspection (tk_plan_*_info / _count, tk_lattice_tiling).
  */
 #ifndef TETRAKIS_B200_H
 #define TETRAKIS_B200_H

@@ -372,3 +372,35 @@ def test_fused_pass_with_defects_algebra_matches_the_oracle(kw):
             ub, upb = ca * ub + cb * upb + coeff * (ub.sum(2, keepdims=True) + tabR[k][:, None, :] + tabC[k][None, :, :]), ub
         u, up = np.where(cross, uc, ub), np.where(cross, upc, upb)
     assert np.abs(u.reshape(-1) - ref["u"]).max() <= 1e-13 * np.abs(ref["u"]).max()
+
+
+def test_header_compiles_as_plain_c_and_links_against_the_library(tmp_path):
+    """include/tetrakis_b200.h is a C header (extern "C", plain pointers): a C program compiled with gcc links
+    against the shared library and calls the entry points that need no device."""
+    import shutil
+    import subprocess
+
+    from tetrakis_sim_b200 import _build
+
+    gcc = shutil.which("gcc")
+    if gcc is None or not os.path.exists(_build.LIB_PATH):
+        pytest.skip("needs gcc and the built library")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "tetrakis_b200.h"\n'
+        "int main(void) {\n"
+        "    int n = -1;\n"
+        "    int rc = tk_device_count(&n);\n"
+        "    tk_plan *plan = 0;\n"
+        "    int rc2 = tk_sheet_band_plan_create(0, 64, 0, 32, &plan);  /* no device here: must fail, not crash */\n"
+        '    printf("%d %d %d %d\\n", tk_abi_version(), rc, n, rc2 != TK_OK || plan != 0);\n'
+        "    if (plan) tk_plan_destroy(plan);\n"
+        "    return 0;\n}\n"
+    )
+    exe = tmp_path / "abi"
+    inc = os.path.join(os.path.dirname(_build.HERE), "include")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           "-L", _build.LIB_DIR, "-ltetrakis_b200", f"-Wl,-rpath,{_build.LIB_DIR}"])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[0]) == 1  # TK_ABI_VERSION
+    assert int(out[3]) == 1

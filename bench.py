@@ -344,7 +344,8 @@ def gpu_single(args, dist=None, emit=True):
                      "traffic": None if f32 else ncu_traffic(workload + ("-fused" if fk else "")),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes / kernel_launches,
-                     "kernel": "lat_step_f32_kernel" if f32 else (f"lat_fused2d_kernel (K={fk})" if fk else "lat_step_kernel"),
+                     "kernel": (f"lat_fused2d_kernel{'<float>' if f32 else ''} (K={fk})" if fk
+                                else ("lat_step_f32_kernel" if f32 else "lat_step_kernel")),
                      "bytes_per_update": alg_bytes / (n_updates * args.steps),
                      "kernel_ms_per_launch": kms / kernel_launches,
                      "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0},

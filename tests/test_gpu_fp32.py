@@ -28,6 +28,7 @@ CASES = {
 @pytest.mark.parametrize("steps,tol", [(100, 2e-6), (1000, 2e-5)])
 def test_fp32_mode_tracks_fp64_within_the_stated_tolerance(case, steps, tol, cpl, monkeypatch):
     monkeypatch.setenv("TK_LAT_CPL", str(cpl))  # cells per lane of the fp32 kernel (fp64 run: default tiling)
+    monkeypatch.setenv("TK_LAT_FUSE", "0")      # this test is about the step-by-step fp32 kernel
     kw, damping = CASES[case]
     spec = tk.LatticeSpec(**kw)
     kick = spec.kick_node()
@@ -69,3 +70,22 @@ def test_fp32_plan_state_round_trip_and_slab_planes():
         import networkx as nx
 
         tk.run_wave_sim(nx.path_graph(3), steps=2, dtype="float32")
+
+
+@pytest.mark.parametrize("S,steps,damping", [(512, 100, 0.0), (200, 1000, 0.0), (130, 101, 0.01)])
+def test_fp32_state_with_fused_passes(S, steps, damping):
+    """Defect-free sheets in the fp32 state mode take the K-step passes too: fp64 arithmetic, the state rounded to
+    fp32 once per pass.  Same stated tolerance as the step-by-step fp32 kernel."""
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.kick_node()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        h32 = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, dt=0.05, damping=damping,
+                              dtype="float32", probes=[kick, spec.node(7)])
+        h64 = tk.run_wave_sim(spec, steps=steps, initial_data={kick: 1.0}, dt=0.05, damping=damping,
+                              probes=[kick, spec.node(7)])
+    assert h32.fused["steps_per_pass"] >= 2 and h32.fused["fused_steps"] >= steps - 1
+    tol = 2e-6 if steps <= 101 else 2e-5
+    assert rel_inf(h32.final_state, h64.final_state) < tol
+    assert rel_inf(h32.probe_series, h64.probe_series) < tol
+    assert np.array_equal(h32.final_state, h32.final_state.astype(np.float32).astype(np.float64))

@@ -38,7 +38,7 @@ struct FusedProbes {
 // info_prev (optional) gets zeros: the previous level of a freshly kicked state is empty.
 __global__ void __launch_bounds__(256)
 lat_sparse_sums_kernel(int S, int n, const long long *__restrict__ idx, const double *__restrict__ val,
-                       double *__restrict__ rowinfo, double *__restrict__ colinfo)
+                       int state_is_f32, double *__restrict__ rowinfo, double *__restrict__ colinfo)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= 2 * S * 4) return;
@@ -48,7 +48,7 @@ lat_sparse_sums_kernel(int S, int n, const long long *__restrict__ idx, const do
     for (int i = 0; i < n; ++i) {
         const long long cell = idx[i] >> 2;
         const int kq = (int)(idx[i] & 3), r = (int)(cell / S), c = (int)(cell % S);
-        if (kq == q && (is_col ? c : r) == line) a += val[i];
+        if (kq == q && (is_col ? c : r) == line) a += state_is_f32 ? (double)(float)val[i] : val[i];  // as stored
     }
     (is_col ? colinfo : rowinfo)[(size_t)line * 8 + q] = a;
 }
@@ -260,9 +260,11 @@ lat_tables_kernel(int S, int nrows, int K, double coeff, double damping, double 
 // per lane (256-bit loads/stores), like lat_step_kernel.  Shared memory holds the two response vectors
 // (y_K, y_{K-1}) of the CTA's rows and columns: (rows + columns) x 64 bytes, whatever K is.
 //   ua: in u_t,     out u_{t+K}      ub: in u_{t-1}, out u_{t+K-1}
-template <int MINB, bool UNDAMPED>
+//   T = double, or float for the optional fp32 state mode (arithmetic, sums and responses stay fp64; the state is
+//   rounded to fp32 once per pass, not once per step)
+template <int MINB, bool UNDAMPED, typename T = double>
 __global__ void __launch_bounds__(256, MINB)
-lat_fused2d_kernel(int S, int nrows, int K, double *__restrict__ ua, double *__restrict__ ub, const double *__restrict__ respR,
+lat_fused2d_kernel(int S, int nrows, int K, T *__restrict__ ua, T *__restrict__ ub, const double *__restrict__ respR,
                    const double *__restrict__ respC, double *__restrict__ prow_a, double *__restrict__ pcol_a,
                    double *__restrict__ prow_b, double *__restrict__ pcol_b, double ca, double cb, double coeff,
                    int rchunk, int nchunk, int nsegk, int nct, int pf_rows,
@@ -306,9 +308,17 @@ lat_fused2d_kernel(int S, int nrows, int K, double *__restrict__ ua, double *__r
         const size_t off = ((size_t)r * S + c0) * 4;
         double u[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0};
         if (valid) {
-            ld256_cs(ua + off, u);
-            ld256_cs(ub + off, up);
-            if (pf_rows > 0 && r + pf_rows < r_end && (lane & 3) == 0) {
+            if constexpr (sizeof(T) == 8) {
+                ld256_cs(reinterpret_cast<const double *>(ua) + off, u);
+                ld256_cs(reinterpret_cast<const double *>(ub) + off, up);
+            } else {
+                const float4 fa = ld128_cs(reinterpret_cast<const float *>(ua) + off);
+                const float4 fb = ld128_cs(reinterpret_cast<const float *>(ub) + off);
+                u[0] = fa.x; u[1] = fa.y; u[2] = fa.z; u[3] = fa.w;
+                up[0] = fb.x; up[1] = fb.y; up[2] = fb.z; up[3] = fb.w;
+            }
+            // one L2 prefetch request per 128-byte line: 4 lanes of 32-byte cells, 8 lanes of 16-byte cells
+            if (pf_rows > 0 && r + pf_rows < r_end && (lane & (sizeof(T) == 8 ? 3 : 7)) == 0) {
                 prefetch_l2(ua + off + (size_t)pf_rows * S * 4);
                 prefetch_l2(ub + off + (size_t)pf_rows * S * 4);
             }
@@ -378,8 +388,18 @@ lat_fused2d_kernel(int S, int nrows, int K, double *__restrict__ ua, double *__r
             up[0] += rb01.x + cb01.x; up[1] += rb01.y + cb01.y; up[2] += rb23.x + cb23.x; up[3] += rb23.y + cb23.y;
         }
         if (valid) {
-            st256_cs(ua + off, u);
-            st256_cs(ub + off, up);
+            if constexpr (sizeof(T) == 8) {
+                st256_cs(reinterpret_cast<double *>(ua) + off, u);
+                st256_cs(reinterpret_cast<double *>(ub) + off, up);
+            } else {
+                const float4 fa = make_float4((float)u[0], (float)u[1], (float)u[2], (float)u[3]);
+                const float4 fb = make_float4((float)up[0], (float)up[1], (float)up[2], (float)up[3]);
+                st128_cs(reinterpret_cast<float *>(ua) + off, fa);
+                st128_cs(reinterpret_cast<float *>(ub) + off, fb);
+                // the sums below must be those of the stored state
+                u[0] = fa.x; u[1] = fa.y; u[2] = fa.z; u[3] = fa.w;
+                up[0] = fb.x; up[1] = fb.y; up[2] = fb.z; up[3] = fb.w;
+            }
         } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {

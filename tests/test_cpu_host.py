@@ -404,3 +404,19 @@ def test_header_compiles_as_plain_c_and_links_against_the_library(tmp_path):
     out = subprocess.check_output([str(exe)], text=True).split()
     assert int(out[0]) == 1  # TK_ABI_VERSION
     assert int(out[3]) == 1
+
+
+def test_sharded_sheet_entry_point_fails_loudly_without_a_device():
+    """No CPU fallback on the multi-GPU sheet path either: without a CUDA device the band plan cannot be created."""
+    import warnings
+
+    try:
+        n = tk.device_count()
+    except Exception:
+        n = 0
+    if n:
+        pytest.skip("a CUDA device is present")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        with pytest.raises((tk.NoDeviceError, tk.TkError, tk.BackendUnavailable)):
+            tk.run_sheet_sharded(64, 8, {0: 1.0}, dt=0.05)

@@ -420,3 +420,88 @@ def test_sharded_sheet_entry_point_fails_loudly_without_a_device():
         warnings.simplefilter("ignore", RuntimeWarning)
         with pytest.raises((tk.NoDeviceError, tk.TkError, tk.BackendUnavailable)):
             tk.run_sheet_sharded(64, 8, {0: 1.0}, dt=0.05)
+
+
+@pytest.mark.parametrize("kw", [dict(defect="blackhole", radius=2.6),
+                                dict(defect="singularity", radius=2.0, mass=2000.0, prune_edges=True),
+                                dict(defect="singularity", radius=2.5, mass=50.0, potential=2.0),
+                                dict(defect="wedge")])
+def test_fused_pass_with_defects_algebra_in_three_dimensions(kw):
+    """The same groundwork for 3-D lattices (configs 3 and 4): the cross is the (r, c) projection of the defect
+    over all layers, the bulk part of a line sum picks up its z neighbours' bulk parts,
+        B+[z] = ca_z B[z] + cb B-[z] + coeff (sum_q B[z] + n_bulk LineSum[z] + crossing sums over the bulk + B[z-1] + B[z+1]),
+    ca_z = (2 - g) - coeff (2S + 4 + number of z neighbours), and a bulk z column evolves on its own given the
+    recorded sums (cell + z stencil only).  NumPy, against the oracle's step-by-step run."""
+    from oracle import wave_oracle as wo
+
+    S, L, steps, K, g = 14, 5, 18, 6, 0.01
+    coeff = 0.9 / (2 * S + 3)
+    spec = tk.LatticeSpec(size=S, dim=3, layers=L, **kw)
+    n, shp = spec.num_slots, (L, S, S, 4)
+    flags, im, pot = np.full(n, 3, np.uint8), np.ones(n), np.zeros(n)
+    si, sf, sm, sv = spec.specials()
+    flags[si], im[si], pot[si] = sf, sm, sv
+    corr = spec.corrections()
+    u0 = np.zeros(n)
+    kick = spec.index(spec.kick_node())
+    u0[kick], u0[(kick + 4 * S * 3 + 9) % n] = 1.0, -0.3
+    u0[(flags & 1) == 0] = 0.0
+    ref = wo.run_structured(S, L, flags, im, pot, corr, u0, steps, coeff, g)
+
+    P, A = ((flags >> 1) & 1).reshape(shp).astype(float), (flags & 1).reshape(shp).astype(float)
+    IM, V = im.reshape(shp), pot.reshape(shp)
+    special = (P.min(3) < 1) | (A.min(3) < 1) | (IM.min(3) != 1) | (IM.max(3) != 1) | (np.abs(V).max(3) > 0)
+    for a_, b_, _ in corr:
+        for x in (a_ // 4, b_ // 4):
+            special[x // (S * S), (x // S) % S, x % S] = True
+    Rd, Cd = special.any((0, 2)), special.any((0, 1))
+    cross = np.broadcast_to((Rd[:, None] | Cd[None, :])[None, :, :, None], shp)
+    n_bulk_cols, n_bulk_rows = (~Cd).sum(), (~Rd).sum()
+
+    def zsum(x):  # x[z-1] + x[z+1], nothing beyond the ends
+        out = np.zeros_like(x)
+        out[1:] += x[:-1]
+        out[:-1] += x[1:]
+        return out
+
+    deg = (P * ((P.sum(3, keepdims=True) - 1) + (P.sum(2, keepdims=True) - 1) + (P.sum(1, keepdims=True) - 1)
+                + zsum(P))).reshape(-1)
+    for a_, _, s_ in corr:
+        deg[a_] += s_
+    deg = deg.reshape(shp)
+    nz = np.array([(z > 0) + (z < L - 1) for z in range(L)], dtype=float)
+    ca, cb = (2 - g) - coeff * (2 * S + 4 + nz), -(1 - g)
+    ca4, ca3 = ca.reshape(L, 1, 1, 1), ca.reshape(L, 1, 1)
+
+    def step_general(u, up, RS, CS):
+        pu = P * u
+        cell = pu.sum(3, keepdims=True)
+        lap = (P * ((cell - u) + (RS[:, :, None, :] - u) + (CS[:, None, :, :] - u) + zsum(pu)) - deg * u).reshape(-1)
+        for a_, b_, s_ in corr:
+            lap[a_] += s_ * u.reshape(-1)[b_]
+        return (2 * u - up + coeff * IM * lap.reshape(shp) - coeff * V * u - g * (u - up)) * A
+
+    u, up = u0.reshape(shp).copy(), np.zeros(shp)
+    for _ in range(steps // K):
+        B, Bp = (u * ~cross).sum(2), (up * ~cross).sum(2)  # [z, r, q]
+        D, Dp = (u * ~cross).sum(1), (up * ~cross).sum(1)  # [z, c, q]
+        uc, upc, tabR, tabC = u.copy(), up.copy(), [], []
+        for _k in range(K):
+            RS, CS = B + (P * uc * cross).sum(2), D + (P * uc * cross).sum(1)
+            tabR.append(RS)
+            tabC.append(CS)
+            un = step_general(uc, upc, RS, CS)
+            Bn = ca3 * B + cb * Bp + coeff * (B.sum(2, keepdims=True) + n_bulk_cols * RS
+                                              + CS[:, ~Cd].sum(1)[:, None, :] + zsum(B))
+            Dn = ca3 * D + cb * Dp + coeff * (D.sum(2, keepdims=True) + n_bulk_rows * CS
+                                              + RS[:, ~Rd].sum(1)[:, None, :] + zsum(D))
+            Bn[:, Rd], Dn[:, Cd] = 0.0, 0.0
+            Bp, B, Dp, D = B, Bn, D, Dn
+            upc, uc = np.where(cross, uc, upc), np.where(cross, un, uc)
+        ub, upb = np.where(cross, 0.0, u), np.where(cross, 0.0, up)  # bulk z columns only
+        for k in range(K):
+            unb = ca4 * ub + cb * upb + coeff * (ub.sum(3, keepdims=True) + tabR[k][:, :, None, :]
+                                                 + tabC[k][:, None, :, :] + zsum(ub))
+            upb, ub = ub, np.where(cross, 0.0, unb)
+        u, up = np.where(cross, uc, ub), np.where(cross, upc, upb)
+    assert np.abs(u.reshape(-1) - ref["u"]).max() <= 1e-13 * np.abs(ref["u"]).max()

@@ -163,6 +163,19 @@ int tk_plan_launch_count(const tk_plan *plan, int64_t *launches);
 int tk_plan_fused_info(tk_plan *plan, int32_t *steps_per_pass, int64_t *fused_steps, int32_t *rows_per_cta,
                        int32_t *ctas_per_sm);
 
+/* Lattices WITH defects (defects.py:55-107, 110-135, 194-247) and 3-D lattices (lattice.py:68-72): tk_plan_run
+ * advances them in K-step passes too, with the "cross" scheme -- the rows and columns that hold a special cell in
+ * any layer (plus those of the probes) are stepped one step at a time together with every row / column sum, whose
+ * bulk parts obey closed recurrences; the rest of the lattice (every (r, c) column of cells is then an independent
+ * chain along z) takes ONE pass per K steps: 32 B per bulk node + 24 B x K per cross node instead of 24 B x K per
+ * node.  Used when the plan owns the whole lattice, the cross covers < 40 % of it, the lattice has >= 2^21 nodes,
+ * and neither a full history nor the energy series is requested; tk_plan_fused_info reports K and the fused steps.
+ * This call adds how large the cross was (rows, columns, fraction of the lattice) and how many passes ran since the
+ * bulk parts were last summed from the data (3-D: every TK_FX_RESYNC = 16 passes; 2-D: every pass).
+ * Environment: TK_LAT_FUSE (0 off; 3-D passes come in 8 or 16 steps), TK_FX_MAXFRAC (percent), TK_FX_MIN_NODES. */
+int tk_plan_cross_info(tk_plan *plan, int32_t *steps_per_pass, int32_t *cross_rows, int32_t *cross_cols,
+                       double *cross_fraction, int64_t *passes_since_anchor);
+
 /* ------------------------------------------------------------------------------------------
  * ONE defect-free sheet sharded over GPUs by rows (one process per GPU).  Rank g holds rows
  * [row_begin, row_end) of the size x size sheet (node index = ((r - row_begin)*size + c)*4 + q).  Row sums are

@@ -87,7 +87,7 @@ def test_fused_passes_equal_the_step_by_step_kernel(graph, monkeypatch):
     assert (b.fused["steps_per_pass"], b.fused["fused_steps"]) == _expected(203, 8) == (8, 203)
     assert rel_inf(b.final_state, a.final_state) < 1e-12
     assert rel_inf(b.probe_series, a.probe_series) < 1e-12
-    assert b.metadata["launches"] < a.metadata["launches"]
+    assert b.launches < a.launches
 
 
 def test_fused_passes_continue_from_a_dense_state_with_a_previous_level():

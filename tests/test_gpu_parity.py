@@ -178,7 +178,7 @@ def test_structured_and_graph_kernels_agree_on_a_medium_singularity_lattice():
     idx = np.array([spec.index(n) for n in a.nodes])
     assert rel_inf(c.array[:, idx], a.array) < 1e-12
     assert a.metadata == b.metadata
-    assert {k: v for k, v in c.metadata.items() if k != "launches"} == a.metadata
+    assert c.metadata == a.metadata  # the reference's keys only; launch counts live in hist.launches
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 51, 64, 1000, 10001])

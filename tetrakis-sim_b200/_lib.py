@@ -23,7 +23,7 @@ ABI_SYMBOLS = (
     "tk_graph_plan_create", "tk_lattice_plan_create", "tk_lattice_plan_create_ex",
     "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
-    "tk_plan_run", "tk_plan_set_probes", "tk_plan_read_probes", "tk_plan_launch_count", "tk_plan_fused_info", "tk_plan_destroy",
+    "tk_plan_run", "tk_plan_set_probes", "tk_plan_read_probes", "tk_plan_launch_count", "tk_plan_fused_info", "tk_plan_cross_info", "tk_plan_destroy",
     "tk_sheet_band_plan_create", "tk_sheet_exchange_doubles", "tk_sheet_pass_local", "tk_sheet_pass_commit", "tk_sheet_kernel_ms",
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
     "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
@@ -109,6 +109,8 @@ def lib():
     L.tk_plan_read_probes.argtypes = [P, P, POINTER(c_int64)]
     L.tk_plan_launch_count.argtypes = [P, POINTER(c_int64)]
     L.tk_plan_fused_info.argtypes = [P, POINTER(c_int32), POINTER(c_int64), POINTER(c_int32), POINTER(c_int32)]
+    L.tk_plan_cross_info.argtypes = [P, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_double),
+                                     POINTER(c_int64)]
     L.tk_sheet_band_plan_create.argtypes = [c_int, c_int32, c_int32, c_int32, POINTER(P)]
     L.tk_sheet_exchange_doubles.argtypes = [P, POINTER(c_int64)]
     L.tk_sheet_pass_local.argtypes = [P, c_int32, c_double, c_double, c_void_p]
@@ -297,6 +299,16 @@ class Plan:
         k, n, r, o = c_int32(0), c_int64(0), c_int32(0), c_int32(0)
         check(lib().tk_plan_fused_info(self._h, ctypes.byref(k), ctypes.byref(n), ctypes.byref(r), ctypes.byref(o)))
         return {"steps_per_pass": k.value, "fused_steps": n.value, "rows_per_cta": r.value, "ctas_per_sm": o.value}
+
+    @property
+    def cross(self) -> dict:
+        """The cross scheme of the last run() (lattices with defects / 3-D): steps per pass (0 = not used), rows and
+        columns of the cross, the fraction of the lattice it covers."""
+        k, r, c, f, n = c_int32(0), c_int32(0), c_int32(0), c_double(0.0), c_int64(0)
+        check(lib().tk_plan_cross_info(self._h, ctypes.byref(k), ctypes.byref(r), ctypes.byref(c), ctypes.byref(f),
+                                       ctypes.byref(n)))
+        return {"steps_per_pass": k.value, "cross_rows": r.value, "cross_cols": c.value, "cross_fraction": f.value,
+                "passes_since_anchor": n.value}
 
     @property
     def tiling(self) -> dict:

@@ -1,0 +1,457 @@
+// K leapfrog steps per pass on lattices WITH defects and on 3-D lattices: the "cross" scheme.
+//
+// Reference operator: tetrakis_sim/lattice.py:30-73 (cell / row / column cliques + vertical links) with the
+// defects of tetrakis_sim/defects.py:55-107 (wedge), 110-135 (black hole), 194-247 (singularity); update:
+// tetrakis_sim/physics.py:119-126.
+//
+// Let R_d / C_d be the rows / columns that contain a special cell in ANY layer (removed, pruned or tagged
+// node, an edge correction, or a probe -- probes are made part of the cross so that their value exists at
+// every step).  The "cross" = all cells with r in R_d or c in C_d, every layer; the rest is the "bulk".
+// Every bulk cell is plain (degree 2S+1+nz, unit mass, no potential) and its row and column are complete
+// cliques, so with RS / CS the total row / column sums its update is
+//     u+ = ca_z u + cb u- + coeff (cell + RS[z,r,q] + CS[z,c,q] + u(z-1) + u(z+1)),
+//     ca_z = (2-g) - coeff (2S+4+nz),  cb = -(1-g).
+// A pass of K steps has two stages:
+//   1. the CROSS STAGE advances, one step at a time, the cross cells (general update, in place in the state
+//      buffers: fx_cross_step_kernel) together with every line sum (fx_lines_kernel).  A line sum splits into the
+//      part over cross cells, summed from the data, and the part B over bulk cells, which obeys a closed
+//      recurrence (sum the bulk update over the bulk cells of the line):
+//          B+[z,r,q] = ca_z B + cb B- + coeff (sum_q' B[q'] + n_bulk_cols RS[z,r,q] + sum_{c bulk} CS[z,c,q]
+//                                              + B[z-1,r,q] + B[z+1,r,q])          (same for columns, D);
+//      alongside, the response y of a bulk z-column at rest to the forcing coeff * RS_k (resp. coeff * CS_k):
+//          y+[z] = ca_z y + cb y- + coeff (sum_q y + X_k[z,line,q] + y[z-1] + y[z+1]),   y_0 = y_{-1} = 0;
+//   2. the BULK PASS: every bulk (r, c) z-column evolves on its own (cell coupling + z stencil) for K steps
+//      without the line terms, then adds the row and column responses y_K / y_{K-1} (the update is linear):
+//      2-D: lat_fused2d_kernel<CROSS> (kernels_fused.cuh); 3-D: fx_bulk3d_kernel below, which streams along z with
+//      a K-level register pipeline (no halo, no redundant work, in place).
+// Traffic per K steps: 32 B per bulk node + 24 B x K per cross node, instead of 24 B x K per node.
+// Derivation restated in NumPy against the oracle: tests/test_cpu_host.py::test_fused_pass_with_defects_algebra_*.
+#pragma once
+#include "common.cuh"
+#include "kernels_lattice.cuh"
+
+namespace tk {
+
+struct FxDev {
+    int S, L;
+    int nR, nC;      // rows / columns of the cross
+    int nbr, nbc;    // bulk rows / columns (S - nR, S - nC)
+    const int *rd_list, *cd_list, *br_list;      // cross rows, cross columns, bulk rows (ascending)
+    const unsigned char *rowflag, *colflag;      // [S] 1 = in the cross
+    const int *rowslot, *colslot;                // [S] index into rd_list / br_list, cd_list / (unused)
+    // partial sums of the participation-masked cross cells written by fx_cross_step_kernel
+    int nsegR, nchR, rcR;   // row band: 32-cell segments per row, row chunks, rows per chunk
+    int nsegC, nchC, rcC;   // column band: segments of cd_list, chunks of bulk rows, rows per chunk
+    double *prowX;  // [L][nR][nsegR][4]
+    double *pcolX;  // [L][nchR][S][4]
+    double *prowC;  // [L][nbr][nsegC][4]
+    double *pcolC;  // [L][nchC][nC][4]
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Cross stage, cells: one leapfrog step (MODE 0) or the sums only (MODE 1) of the cross cells.
+// A warp task = (layer, 32-cell segment, row chunk) of the ROW BAND (rows of R_d, all columns) or of the
+// COLUMN BAND (bulk rows, columns of C_d); one cell per lane (256-bit accesses), marching down the chunk's rows
+// like lat_step_kernel: column sums in registers, one transposing butterfly per row for the row sums.
+// rowinfo / colinfo hold the TOTAL line sums of the state being read (fx_lines_kernel) + the static counts.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+fx_cross_step_kernel(const __grid_constant__ LatDev P, const __grid_constant__ FxDev X,
+                     const double *__restrict__ u, double *__restrict__ w, double coeff, double damping,
+                     long long ntaskR, long long ntaskC)
+{
+    constexpr bool STEP = MODE == 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long task = (long long)blockIdx.x * 8 + warp;
+    const bool band = task >= ntaskR;  // false: row band, true: column band
+    if (band) task -= ntaskR;
+    if (task >= (band ? ntaskC : ntaskR)) return;  // whole warp; no block-level sync below
+    const int S = P.S, L = P.Lloc;
+    const int zl = (int)(task % L);
+    task /= L;
+    const int nseg = band ? X.nsegC : X.nsegR;
+    const int seg = (int)(task % nseg), ch = (int)(task / nseg);
+    const int rc = band ? X.rcC : X.rcR, nrows = band ? X.nbr : X.nR, nch = band ? X.nchC : X.nchR;
+    const int ncolb = band ? X.nC : S;
+    const int *__restrict__ rlist = band ? X.br_list : X.rd_list;
+    const int j = seg * 32 + lane;
+    const bool valid = j < ncolb;
+    const int c = band ? (valid ? X.cd_list[j] : 0) : j;
+
+    const size_t plane = (size_t)S * S * 4;
+    const size_t zbase = (size_t)(zl + P.halo) * plane;
+    const unsigned fplain = plain_flags(P, zl);
+    const bool zm_on = P.halo && (fplain & 0x100u), zp_on = P.halo && (fplain & 0x1000u);
+    const double degbase = 4.0 + (zm_on ? 1.0 : 0.0) + (zp_on ? 1.0 : 0.0);
+
+    double CS[4] = {0, 0, 0, 0}, CC[4] = {0, 0, 0, 0}, cacc[4] = {0, 0, 0, 0};
+    if (STEP && valid) {
+        ld256_nc(P.colinfo + ((size_t)zl * S + c) * 8, CS);
+        ld256_nc(P.colinfo + ((size_t)zl * S + c) * 8 + 4, CC);
+    }
+    const int i_begin = ch * rc, i_end = min(nrows, i_begin + rc);
+    const int tab0 = c / kTabSeg;
+    double *__restrict__ prow = band ? X.prowC : X.prowX;
+    for (int i = i_begin; i < i_end; ++i) {
+        const int r = rlist[i];
+        const size_t off = zbase + ((size_t)r * S + c) * 4;
+        double uq[4] = {0, 0, 0, 0}, upq[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
+        int det = -1;
+        if (valid) {
+            ld256_nc(u + off, uq);
+            if (STEP) {
+                ld256_cs(w + off, upq);
+                if (zm_on) ld256_nc(u + off - plane, zm);
+                if (zp_on) ld256_nc(u + off + plane, zp);
+            }
+            det = P.seg_flag[((size_t)zl * S + r) * P.ntab + tab0];
+        }
+        const bool all_plain = __all_sync(0xffffffffu, det < 0);
+        double un[4], pun[4];
+        if (!STEP) {
+            unsigned f = fplain;
+            if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + (c & (kTabSeg - 1))];
+            if (!valid) f = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pun[q] = ((f >> q) & 1u) ? uq[q] : 0.0;
+        } else {
+            double RS[4], RC[4];
+            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8, RS);
+            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8 + 4, RC);
+            if (all_plain) {
+                const double cell = (uq[0] + uq[1]) + (uq[2] + uq[3]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double nb = (cell + RS[q]) + (CS[q] + (zm[q] + zp[q]));
+                    const double dg = (RC[q] + degbase) + CC[q];
+                    const double lap = nb - dg * uq[q];
+                    un[q] = 2.0 * uq[q] - upq[q] + coeff * lap - damping * (uq[q] - upq[q]);
+                    pun[q] = valid ? un[q] : 0.0;
+                }
+            } else {
+                unsigned f = fplain;
+                if (det >= 0) f = P.det_flags[(size_t)det * kTabSeg + (c & (kTabSeg - 1))];
+                if (!valid) f = 0;
+                CellIO io;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    io.uq[q] = uq[q]; io.upq[q] = upq[q]; io.zm[q] = zm[q]; io.zp[q] = zp[q];
+                    io.RS[q] = RS[q]; io.RC[q] = RC[q]; io.CS[q] = CS[q]; io.CC[q] = CC[q];
+                }
+                cell_update_detail(P, u, det, c & (kTabSeg - 1), (long long)off, f, coeff, damping, 0.0, io);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { un[q] = io.un[q]; pun[q] = io.pun[q]; }
+            }
+            if (valid) st256(w + off, un);  // the cross is re-read next step: keep it in L2 (no evict-first hint)
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cacc[q] += pun[q];
+        warp_sum4_store(pun, lane, prow + (((size_t)zl * nrows + i) * nseg + seg) * 4);
+    }
+    if (valid) st256((band ? X.pcolC : X.pcolX) + (((size_t)zl * nch + ch) * ncolb + j) * 4, cacc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Cross stage, lines: one thread per (kind, layer, line).  Finishes the sums of the cross parts, advances the
+// bulk parts B (rows) / D (columns) and the responses y by one step (ADVANCE), writes the total line sums
+// X = bulk part + cross part into rowinfo / colinfo, and leaves per-block totals of X over the bulk lines for
+// the next call.  Block 0 also gathers the probes from `state` (the level X describes).
+struct FxLines {
+    int advance;      // 1: B, y <- one step further (from Xprev = rowinfo/colinfo as they are); 0: B is given
+    int first;        // advance only: 1 = first step of a pass, y and y- are zero (whatever the buffers hold);
+                      // 2 = second step, y- is zero
+    double coeff, damping;
+    double *rowinfo, *colinfo;        // [L][S][8] total line sums (0-3) + static counts (4-7)
+    double *Bcur[2], *Bprev[2];       // [kind][L][S][8] bulk parts (stride 8, entries 0-3), two time levels
+    double *ycur[2], *yprev[2];       // [kind][L][S][4] responses
+    const double *tot_in;             // [2][L][nblk][4] per-block totals over bulk lines of the previous X
+    double *tot_out;
+    const void *state;                // probes
+    const long long *probe_idx;
+    int n_probes;
+    double *probe_row;                // row to write (or the base of the series when ctr != null)
+    const long long *ctr;
+};
+
+__global__ void __launch_bounds__(128)
+fx_lines_kernel(const __grid_constant__ FxDev X, const __grid_constant__ FxLines A)
+{
+    __shared__ double tot[4];
+    __shared__ double red[4][128];
+    const int S = X.S, L = X.L, nblk = (S + 127) / 128;
+    int b = blockIdx.x;
+    const int blk = b % nblk;
+    b /= nblk;
+    const int zl = b % L, kind = b / L;
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && A.n_probes > 0) {
+        double *row = A.probe_row;
+        if (A.ctr != nullptr) row += (size_t)A.ctr[0] * A.n_probes;
+        for (int t = tid; t < A.n_probes; t += blockDim.x) row[t] = static_cast<const double *>(A.state)[A.probe_idx[t]];
+    }
+    if (A.advance) {
+        if (tid < 4) {
+            const double *tp = A.tot_in + ((size_t)(1 - kind) * L + zl) * nblk * 4 + tid;
+            double a = 0.0;
+            for (int k = 0; k < nblk; ++k) a += tp[(size_t)k * 4];
+            tot[tid] = a;
+        }
+        __syncthreads();
+    }
+    const int x = blk * 128 + tid;
+    double Xn[4] = {0, 0, 0, 0};
+    bool bulk_line = false;
+    if (x < S) {
+        const bool flag = (kind ? X.colflag : X.rowflag)[x] != 0;
+        const int slot = (kind ? X.colslot : X.rowslot)[x];
+        double *info = (kind ? A.colinfo : A.rowinfo) + ((size_t)zl * S + x) * 8;
+        // cross part of the line sum
+        double cr[4] = {0, 0, 0, 0};
+        if (kind == 0) {
+            const double *pp = flag ? X.prowX + ((size_t)zl * X.nR + slot) * X.nsegR * 4
+                                    : X.prowC + ((size_t)zl * X.nbr + slot) * X.nsegC * 4;
+            const int n = flag ? X.nsegR : X.nsegC;
+            for (int s = 0; s < n; ++s)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cr[q] += pp[(size_t)s * 4 + q];
+        } else {
+            for (int k = 0; k < X.nchR; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cr[q] += X.pcolX[(((size_t)zl * X.nchR + k) * S + x) * 4 + q];
+            if (flag)
+                for (int k = 0; k < X.nchC; ++k)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cr[q] += X.pcolC[(((size_t)zl * X.nchC + k) * X.nC + slot) * 4 + q];
+        }
+        if (!flag) {
+            bulk_line = true;
+            const size_t li = (size_t)zl * S + x;
+            double Bn[4];
+            if (A.advance) {
+                const double *Bc = A.Bcur[kind], *Bp = A.Bprev[kind];
+                const double nz = (zl > 0 ? 1.0 : 0.0) + (zl < L - 1 ? 1.0 : 0.0);
+                const double caz = (2.0 - A.damping) - A.coeff * (2.0 * S + 4.0 + nz), cb = -(1.0 - A.damping);
+                const double nb = (double)(kind ? X.nbr : X.nbc);
+                double bc[4], bp[4], zs[4] = {0, 0, 0, 0}, xp[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    bc[q] = Bc[li * 8 + q];
+                    bp[q] = Bp[li * 8 + q];
+                    xp[q] = info[q];
+                    if (zl > 0) zs[q] += Bc[(li - S) * 8 + q];
+                    if (zl < L - 1) zs[q] += Bc[(li + S) * 8 + q];
+                }
+                const double sb = (bc[0] + bc[1]) + (bc[2] + bc[3]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    Bn[q] = caz * bc[q] + cb * bp[q] + A.coeff * (((sb + nb * xp[q]) + tot[q]) + zs[q]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) A.Bprev[kind][li * 8 + q] = Bn[q];  // becomes "cur" after the host's swap
+                // response of a bulk z-column at rest to the forcing coeff * X_k of this line
+                double yc[4] = {0, 0, 0, 0}, yp[4] = {0, 0, 0, 0}, ys[4] = {0, 0, 0, 0};
+                if (A.first != 1) {
+                    const double *Yc = A.ycur[kind], *Yp = A.yprev[kind];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        yc[q] = Yc[li * 4 + q];
+                        yp[q] = A.first == 2 ? 0.0 : Yp[li * 4 + q];
+                        if (zl > 0) ys[q] += Yc[(li - S) * 4 + q];
+                        if (zl < L - 1) ys[q] += Yc[(li + S) * 4 + q];
+                    }
+                }
+                const double sy = (yc[0] + yc[1]) + (yc[2] + yc[3]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    A.yprev[kind][li * 4 + q] = caz * yc[q] + cb * yp[q] + A.coeff * ((sy + xp[q]) + ys[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) Bn[q] = A.Bcur[kind][li * 8 + q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Xn[q] = Bn[q] + cr[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Xn[q] = cr[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) info[q] = Xn[q];
+    }
+    // totals of X over the BULK lines of this block (fixed tree)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) red[q][tid] = bulk_line ? Xn[q] : 0.0;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (tid < o) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red[q][tid] += red[q][tid + o];
+        }
+        __syncthreads();
+    }
+    if (tid < 4) A.tot_out[(((size_t)kind * L + zl) * nblk + blk) * 4 + tid] = red[tid][0];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Bulk parts of the line sums straight from a state buffer (entering the fused mode, periodic re-anchoring in
+// 3-D): warp = (layer, 32-cell segment, row chunk) marching down the chunk, cross rows / columns masked out.
+// Partials go to prow [L][S][nseg32][4] / pcol [L][nchunk][S][4] and are summed by lat_finalise_kernel.
+__global__ void __launch_bounds__(256)
+fx_bulk_sums_kernel(const __grid_constant__ FxDev X, int halo, const double *__restrict__ u, double *__restrict__ prow,
+                    double *__restrict__ pcol, int rchunk, int nchunk, int nseg, long long ntask)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long task = (long long)blockIdx.x * 8 + warp;
+    if (task >= ntask) return;
+    const int S = X.S, L = X.L;
+    const int zl = (int)(task % L);
+    task /= L;
+    const int seg = (int)(task % nseg), ch = (int)(task / nseg);
+    const int c = seg * 32 + lane;
+    const bool use = c < S && !X.colflag[min(c, S - 1)];
+    const size_t zbase = (size_t)(zl + halo) * S * S * 4;
+    double cacc[4] = {0, 0, 0, 0};
+    const int r_end = min(S, (ch + 1) * rchunk);
+    for (int r = ch * rchunk; r < r_end; ++r) {
+        double v[4] = {0, 0, 0, 0};
+        if (use && !X.rowflag[r]) ld256_nc(u + zbase + ((size_t)r * S + c) * 4, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cacc[q] += v[q];
+        warp_sum4_store(v, lane, prow + (((size_t)zl * S + r) * nseg + seg) * 4);
+    }
+    if (c < S) st256(pcol + (((size_t)zl * nchunk + ch) * S + c) * 4, cacc);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 3-D bulk pass: K steps of every bulk (r, c) z-column in ONE streaming sweep along z.
+//
+// Thread = one Hadamard mode of one cell: lanes 4j..4j+3 of a warp hold the four quadrant values of cell j and
+// turn them into the sum mode + three difference modes with two xor-shuffle rounds; the cell operator
+// ca I + coeff J acts as ca + 4 coeff on the sum mode and as ca on the others, and the vertical links do not mix
+// quadrants, so each mode is an independent 1-D recurrence along z:
+//     A_k(z) = lam A_{k-1}(z) + cb A_{k-2}(z) + coeff (A_{k-1}(z-1) + A_{k-1}(z+1)),
+// with lam taken for two vertical neighbours and the end layers mirrored (a missing neighbour contributes
+// "itself": -coeff u + coeff u = 0, which is the end layer's degree).  The thread sweeps z once with a pipeline of
+// K levels in registers: at tick t it loads layer t of u_t / u_{t-1} and level k advances to layer t-k, so level K
+// of layer t-K and level K-1 of the same layer leave the pipeline and are stored in place -- every one of the K
+// updates of every node is computed, no intermediate state is stored, there is no halo and no redundant work.
+// Window of level j: slot (t mod 3) receives layer t-j, slots (t+2) mod 3 / (t+1) mod 3 hold layers t-j-1 / t-j-2.
+// The responses of the row and the column (fx_lines_kernel) are added as the values leave the pipeline.
+//   in_a / in_b : u_t / u_{t-1};  out_a / out_b : where u_{t+K} / u_{t+K-1} go (the same two buffers, swapped when
+//   K is odd).  A thread only ever touches its own (r, c) column, layer t-K after reading layer t: in place is safe.
+template <int K, bool UNDAMPED>
+struct FxPipe {
+    double w[K][3];
+    double mprev, mcur;  // level -1 at layers t-1, t
+};
+
+template <int K, bool UNDAMPED, int R, bool GUARD>
+__device__ __forceinline__ void fx_tick(FxPipe<K, UNDAMPED> &p, int t, int L, double lam, double cb, double coeff,
+                                        double in0, double inm, double &outK, double &outK1)
+{
+    constexpr int SN = R % 3, SB = (R + 2) % 3, SA = (R + 1) % 3;  // newest, middle, oldest slot of this tick
+    p.mprev = p.mcur;
+    p.mcur = inm;
+    p.w[0][SN] = in0;
+#pragma unroll
+    for (int k = 1; k <= K; ++k) {
+        // level k at layer x = t - k from level k-1 at x-1, x, x+1 and level k-2 at x
+        double a = p.w[k - 1][SA], b = p.w[k - 1][SB], c = p.w[k - 1][SN];
+        const double prev = k >= 2 ? p.w[k - 2][SA] : p.mprev;
+        if (GUARD) {
+            const int x = t - k;
+            if (x <= 0) a = b;        // mirror below the first layer (uniform over the grid)
+            if (x >= L - 1) c = b;    // mirror above the last layer
+        }
+        double n;
+        if (UNDAMPED) n = fma(lam, b, -prev);
+        else n = fma(lam, b, cb * prev);
+        n = fma(coeff, a, n);
+        n = fma(coeff, c, n);
+        if (k < K) p.w[k][SN] = n;
+        else outK = n;
+    }
+    outK1 = p.w[K - 1][SB];  // level K-1 at layer t-K (computed one tick ago)
+}
+
+__device__ __forceinline__ double hadamard4(double v, int lane)
+{
+    double t = __shfl_xor_sync(0xffffffffu, v, 1);
+    v = (lane & 1) ? t - v : v + t;
+    t = __shfl_xor_sync(0xffffffffu, v, 2);
+    v = (lane & 2) ? t - v : v + t;
+    return v;
+}
+
+template <int K, bool UNDAMPED, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+fx_bulk3d_kernel(const __grid_constant__ FxDev X, int halo, const double *in_a, const double *in_b, double *out_a,
+                 double *out_b, const double *__restrict__ yRa, const double *__restrict__ yRb,
+                 const double *__restrict__ yCa, const double *__restrict__ yCb, double ca, double cb, double coeff,
+                 int nct, int pf_layers)
+{
+    const int S = X.S, L = X.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ct = blockIdx.x % nct;
+    const int bi = blockIdx.x / nct;
+    const int r = X.br_list[bi];  // bulk rows only
+    const int c = ct * 64 + warp * 8 + (lane >> 2), m = lane & 3;
+    const bool act = c < S && !X.colflag[min(c, S - 1)];
+    // a warp whose 8 cells are all cross cells / beyond the row has nothing to do (no block-level sync below)
+    if (!__any_sync(0xffffffffu, act)) return;
+    const size_t plane = (size_t)S * S * 4;
+    const size_t cell0 = (size_t)halo * plane + ((size_t)r * S + min(c, S - 1)) * 4 + m;
+    const double lam = m == 0 ? ca + 4.0 * coeff : ca;
+    FxPipe<K, UNDAMPED> p;
+#pragma unroll
+    for (int k = 0; k < K; ++k) p.w[k][0] = p.w[k][1] = p.w[k][2] = 0.0;
+    p.mprev = p.mcur = 0.0;
+    const bool pf_lane = pf_layers > 0 && act && (lane & 15) == 0;  // one request per 128-byte line
+    const int nt = L + K;
+    // software pipeline of the loads: the values of tick t+1 are requested before tick t is computed
+    double na = 0.0, nb = 0.0;
+    if (act) {
+        na = in_a[cell0];
+        nb = in_b[cell0];
+    }
+    if (pf_lane)
+        for (int z = 1; z < min(L, 1 + pf_layers); ++z) {
+            prefetch_l2(in_a + cell0 + (size_t)z * plane);
+            prefetch_l2(in_b + cell0 + (size_t)z * plane);
+        }
+    auto tick = [&](auto rot, int t) {
+        constexpr int R = decltype(rot)::value;
+        if (t >= nt) return;
+        // Hadamard modes of the layer loaded for this tick
+        const double h0 = hadamard4(na, lane), hm = hadamard4(nb, lane);
+        if (t + 1 < L && act) {
+            na = in_a[cell0 + (size_t)(t + 1) * plane];
+            nb = in_b[cell0 + (size_t)(t + 1) * plane];
+        } else {
+            na = 0.0;
+            nb = 0.0;
+        }
+        if (pf_lane && t + 1 + pf_layers < L) {
+            prefetch_l2(in_a + cell0 + (size_t)(t + 1 + pf_layers) * plane);
+            prefetch_l2(in_b + cell0 + (size_t)(t + 1 + pf_layers) * plane);
+        }
+        double oK, oK1;
+        if (t > K && t < L) fx_tick<K, UNDAMPED, R, false>(p, t, L, lam, cb, coeff, h0, hm, oK, oK1);
+        else fx_tick<K, UNDAMPED, R, true>(p, t, L, lam, cb, coeff, h0, hm, oK, oK1);
+        const int z = t - K;
+        if (z >= 0) {
+            const double va = 0.25 * hadamard4(oK, lane), vb = 0.25 * hadamard4(oK1, lane);
+            if (act) {
+                const size_t lr = ((size_t)z * S + r) * 4 + m, lc = ((size_t)z * S + c) * 4 + m;
+                out_a[cell0 + (size_t)z * plane] = va + (yRa[lr] + yCa[lc]);
+                out_b[cell0 + (size_t)z * plane] = vb + (yRb[lr] + yCb[lc]);
+            }
+        }
+    };
+#pragma unroll 1
+    for (int t = 0; t < nt; t += 3) {
+        tick(std::integral_constant<int, 0>{}, t);
+        tick(std::integral_constant<int, 1>{}, t + 1);
+        tick(std::integral_constant<int, 2>{}, t + 2);
+    }
+}
+
+}  // namespace tk

@@ -262,14 +262,23 @@ lat_tables_kernel(int S, int nrows, int K, double coeff, double damping, double 
 //   ua: in u_t,     out u_{t+K}      ub: in u_{t-1}, out u_{t+K-1}
 //   T = double, or float for the optional fp32 state mode (arithmetic, sums and responses stay fp64; the state is
 //   rounded to fp32 once per pass, not once per step)
-template <int MINB, bool UNDAMPED, typename T = double>
+//   CROSS (sheets with defects, kernels_cross.cuh): cells of the cross -- rows with rowflag, columns with colflag --
+//   are left alone (the cross stage has already advanced them in place) and do not enter the partial sums, which
+//   then are the BULK parts of the line sums; the responses come from fx_lines_kernel as two plain [line][4] arrays
+//   (respR = y_K, respC = y_K of the columns, respRb / respCb = y_{K-1}); ua / ub are the buffers u_t / u_{t-1} are
+//   read from, oa / ob the ones u_{t+K} / u_{t+K-1} are written to (the same two, swapped when K is odd); probes are
+//   cross cells, so the probe path is off.
+template <int MINB, bool UNDAMPED, typename T = double, bool CROSS = false>
 __global__ void __launch_bounds__(256, MINB)
-lat_fused2d_kernel(int S, int nrows, int K, T *__restrict__ ua, T *__restrict__ ub, const double *__restrict__ respR,
+lat_fused2d_kernel(int S, int nrows, int K, T *ua, T *ub, const double *__restrict__ respR,
                    const double *__restrict__ respC, double *__restrict__ prow_a, double *__restrict__ pcol_a,
                    double *__restrict__ prow_b, double *__restrict__ pcol_b, double ca, double cb, double coeff,
                    int rchunk, int nchunk, int nsegk, int nct, int pf_rows,
                    const __grid_constant__ FusedProbes probes, double *__restrict__ probe_series,
-                   const long long *__restrict__ ctr, long long row0)
+                   const long long *__restrict__ ctr, long long row0,
+                   const unsigned char *__restrict__ rowflag = nullptr, const unsigned char *__restrict__ colflag = nullptr,
+                   const double *__restrict__ respRb = nullptr, const double *__restrict__ respCb = nullptr,
+                   T *oa = nullptr, T *ob = nullptr)
 {
     extern __shared__ __align__(16) unsigned char tk_smem[];
     const int WC = blockDim.x >> 5;
@@ -286,20 +295,27 @@ lat_fused2d_kernel(int S, int nrows, int K, T *__restrict__ ua, T *__restrict__ 
     for (int i = threadIdx.x; i < ncol * 8; i += blockDim.x) {
         const int cl_ = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
         const int c = col0 + cl_;
-        const double v = (c < S && k >= 0) ? respC[((size_t)k * S + c) * 4 + q] : 0.0;
+        double v;
+        if (CROSS) v = c < S ? (j < 4 ? respC : respCb)[(size_t)c * 4 + q] : 0.0;
+        else v = (c < S && k >= 0) ? respC[((size_t)k * S + c) * 4 + q] : 0.0;
         colresp[((size_t)(j >> 1) * ncol + cl_) * 2 + (j & 1)] = v;
     }
     for (int i = threadIdx.x; i < (r_end - r_begin) * 8; i += blockDim.x) {
         const int rl = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
-        rowresp[i] = k >= 0 ? respR[((size_t)k * nrows + r_begin + rl) * 4 + q] : 0.0;
+        if (CROSS) rowresp[i] = (j < 4 ? respR : respRb)[(size_t)(r_begin + rl) * 4 + q];
+        else rowresp[i] = k >= 0 ? respR[((size_t)k * nrows + r_begin + rl) * 4 + q] : 0.0;
     }
     __syncthreads();
+    if (!CROSS) {
+        oa = ua;
+        ob = ub;
+    }
 
     const int segk = ct * WC + warp;
     if (segk >= nsegk) return;
     const int cl = warp * 32 + lane;
     const int c0 = col0 + cl;
-    const bool valid = c0 < S;
+    const bool valid = c0 < S && !(CROSS && colflag[min(c0, S - 1)]);
     long long base_row = row0;
     if (ctr != nullptr) base_row = ctr[0];
     const double lam_m = ca + 4.0 * coeff;
@@ -307,6 +323,11 @@ lat_fused2d_kernel(int S, int nrows, int K, T *__restrict__ ua, T *__restrict__ 
     for (int r = r_begin; r < r_end; ++r) {
         const size_t off = ((size_t)r * S + c0) * 4;
         double u[4] = {0, 0, 0, 0}, up[4] = {0, 0, 0, 0};
+        if (CROSS && rowflag[r]) {  // a row of the cross: nothing to do, its bulk part is empty
+            warp_sum4_store(u, lane, prow_a + ((size_t)r * nsegk + segk) * 4);
+            warp_sum4_store(up, lane, prow_b + ((size_t)r * nsegk + segk) * 4);
+            continue;
+        }
         if (valid) {
             if constexpr (sizeof(T) == 8) {
                 ld256_cs(reinterpret_cast<const double *>(ua) + off, u);
@@ -324,8 +345,10 @@ lat_fused2d_kernel(int S, int nrows, int K, T *__restrict__ ua, T *__restrict__ 
             }
         }
         bool hit = false;
+        if (!CROSS) {
 #pragma unroll 1
-        for (int p = 0; p < probes.n; ++p) hit |= valid && probes.cell[p] == (long long)r * S + c0;
+            for (int p = 0; p < probes.n; ++p) hit |= valid && probes.cell[p] == (long long)r * S + c0;
+        }
         // Cell eigenbasis: the cell operator ca*I + coeff*J (J = all-ones 4x4) acts as (ca + 4 coeff) on the
         // cell mean m and as ca on the deviations d_q = u_q - m (d_3 = -(d_0+d_1+d_2)), so K steps are four
         // independent scalar recurrences y+ = lam*y + cb*y-: one FMA per recurrence and step when damping = 0
@@ -389,13 +412,13 @@ lat_fused2d_kernel(int S, int nrows, int K, T *__restrict__ ua, T *__restrict__ 
         }
         if (valid) {
             if constexpr (sizeof(T) == 8) {
-                st256_cs(reinterpret_cast<double *>(ua) + off, u);
-                st256_cs(reinterpret_cast<double *>(ub) + off, up);
+                st256_cs(reinterpret_cast<double *>(oa) + off, u);
+                st256_cs(reinterpret_cast<double *>(ob) + off, up);
             } else {
                 const float4 fa = make_float4((float)u[0], (float)u[1], (float)u[2], (float)u[3]);
                 const float4 fb = make_float4((float)up[0], (float)up[1], (float)up[2], (float)up[3]);
-                st128_cs(reinterpret_cast<float *>(ua) + off, fa);
-                st128_cs(reinterpret_cast<float *>(ub) + off, fb);
+                st128_cs(reinterpret_cast<float *>(oa) + off, fa);
+                st128_cs(reinterpret_cast<float *>(ob) + off, fb);
                 // the sums below must be those of the stored state
                 u[0] = fa.x; u[1] = fa.y; u[2] = fa.z; u[3] = fa.w;
                 up[0] = fb.x; up[1] = fb.y; up[2] = fb.z; up[3] = fb.w;
@@ -415,7 +438,7 @@ lat_fused2d_kernel(int S, int nrows, int K, T *__restrict__ ua, T *__restrict__ 
         warp_sum4_store(u, lane, prow_a + ((size_t)r * nsegk + segk) * 4);
         warp_sum4_store(up, lane, prow_b + ((size_t)r * nsegk + segk) * 4);
     }
-    if (valid) {
+    if (c0 < S) {
         st256(pcol_a + ((size_t)ch * S + c0) * 4, cacc_a);
         st256(pcol_b + ((size_t)ch * S + c0) * 4, cacc_b);
     }

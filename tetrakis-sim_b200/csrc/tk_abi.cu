@@ -12,6 +12,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "kernels_cross.cuh"
 #include "kernels_ensemble.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_graph.cuh"
@@ -66,15 +67,6 @@ int dev_alloc(T **p, size_t count)
     *p = nullptr;
     if (count == 0) count = 1;
     TK_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
-    return TK_OK;
-}
-
-template <typename T>
-int dev_upload(T **p, const std::vector<T> &v)
-{
-    int rc = dev_alloc(p, v.size());
-    if (rc) return rc;
-    if (!v.empty()) TK_CUDA(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return TK_OK;
 }
 
@@ -156,6 +148,21 @@ struct tk_plan {
     std::vector<long long> probe_idx_host;   // buffer-relative probe indices (fused passes write probes)
     long long fused_steps_last = 0;          // steps the last tk_plan_run advanced with fused passes
     std::vector<long long> dead_local;  // ABI-local indices of removed nodes (for dense set_state)
+
+    // K-step passes on lattices with defects / 3-D lattices: the cross scheme (kernels_cross.cuh, host_cross.inc)
+    std::vector<int> special_rows, special_cols;  // rows / columns holding a special cell in any layer (sorted)
+    bool fx_whole = false;                   // the plan owns the whole lattice (no slab neighbours): eligible
+    bool fx_ready = false;
+    std::vector<long long> fx_probe_key;     // the probe set the cross was built for
+    tk::FxDev fx{};
+    std::vector<void *> fx_owned;            // device allocations of the current cross setup
+    double *fxB[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kind][level slot] bulk parts, [L][S][8]
+    double *fxY[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kind][level slot] responses, [L][S][4]
+    double *fxTot[2] = {nullptr, nullptr};   // per-block totals over bulk lines, two generations
+    int fx_bslot = 0, fx_yslot = 0, fx_tslot = 0;  // which slot is "current"
+    int fx_k_run = 0;                        // steps per pass of the last run (0 = not used)
+    long long fx_passes = 0;                 // passes since the bulk parts were last summed from the data
+    double fx_cross_frac = 0.0;
 };
 
 namespace {
@@ -179,12 +186,20 @@ int plan_common_init(tk_plan *p, int device)
     return TK_OK;
 }
 
+// Uploads and zero-fills of plan-owned memory are ordered on the plan's own stream (a non-blocking stream does
+// not synchronise with the legacy default stream, so cudaMemset / cudaMemcpy there could land after kernels the
+// plan has already enqueued).  The host vector may be a temporary: wait for the copy.
 template <typename T>
 int plan_upload(tk_plan *p, T **dst, const std::vector<T> &v)
 {
-    int rc = dev_upload(dst, v);
-    if (rc == TK_OK) p->owned.push_back((void *)*dst);
-    return rc;
+    int rc = dev_alloc(dst, v.size());
+    if (rc) return rc;
+    p->owned.push_back((void *)*dst);
+    if (!v.empty()) {
+        TK_CUDA(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, p->stream));
+        TK_CUDA(cudaStreamSynchronize(p->stream));
+    }
+    return TK_OK;
 }
 
 template <typename T>
@@ -193,7 +208,7 @@ int plan_alloc(tk_plan *p, T **dst, size_t count, bool zero)
     int rc = dev_alloc(dst, count);
     if (rc) return rc;
     p->owned.push_back((void *)*dst);
-    if (zero) TK_CUDA(cudaMemset(*dst, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    if (zero) TK_CUDA(cudaMemsetAsync(*dst, 0, std::max<size_t>(count, 1) * sizeof(T), p->stream));
     return TK_OK;
 }
 
@@ -206,6 +221,8 @@ int env_int(const char *name, int dflt)
 // The host side is one translation unit split by subject:
 #include "host_launch.inc"
 #include "host_fused.inc"
+#include "host_cross.inc"
+#include "host_device.inc"
 #include "host_plans.inc"
 #include "host_run.inc"
 #include "host_peer.inc"

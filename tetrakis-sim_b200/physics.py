@@ -101,8 +101,9 @@ class _RowView(Mapping):
         return dict(self.items())
 
 
-def _cfl(max_degree: int, c: float, dt: float, steps: int, damping: float):
-    """reference physics.py:64-91: metadata + CFL clamp.  Returns (effective_dt, metadata)."""
+def _cfl(max_degree: int, c: float, dt: float, steps, damping: float):
+    """reference physics.py:64-91: metadata + CFL clamp.  Returns (effective_dt, metadata).
+    ``steps`` is recorded as the caller passed it (the reference stores the requested value, negative or not)."""
     effective_dt = float(dt)
     metadata: dict = {
         "steps": steps,
@@ -132,7 +133,8 @@ def _cfl(max_degree: int, c: float, dt: float, steps: int, damping: float):
     return effective_dt, metadata
 
 
-def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes, energy, reorder="auto"):
+def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes, energy, reorder="auto",
+               steps_requested=None):
     comp: CompiledGraph
     if path == "structured":
         comp = structured_from_graph(G, device=device)
@@ -140,7 +142,8 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
         comp = compile_graph(G, device=device, reorder=reorder)
     try:
         nodes, index = comp.nodes, comp.index
-        effective_dt, metadata = _cfl(comp.max_degree, c, dt, steps, damping)
+        effective_dt, metadata = _cfl(comp.max_degree, c, dt, steps if steps_requested is None else steps_requested,
+                                      damping)
         # physics.py:30-38: zero state, then the user's kicks, else a unit kick at nodes[len//2]
         extra0 = None
         if initial_data:
@@ -187,10 +190,11 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
 
 
 def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device, record, probes, energy,
-                 dtype="float64", snapshot_every=1):
+                 dtype="float64", snapshot_every=1, steps_requested=None):
     plan = compile_lattice(spec, device=device, dtype=dtype)
     try:
-        effective_dt, metadata = _cfl(plan.max_degree, c, dt, steps, damping)
+        effective_dt, metadata = _cfl(plan.max_degree, c, dt, steps if steps_requested is None else steps_requested,
+                                      damping)
         if initial_data:
             kicks = {n: float(v) for n, v in initial_data.items() if spec.contains(n)}
         else:
@@ -216,8 +220,9 @@ def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device,
             hist.final_state = plan.get_state()
         hist.elapsed_ms = out["elapsed_ms"]
         hist.energy = None if out["energy"] is None else out["energy"] * (c * c)
-        hist.metadata["launches"] = plan.launches
-        hist.fused = plan.fused  # defect-free 2-D sheets advance K steps per pass (tk_plan_fused_info)
+        hist.launches = plan.launches  # an attribute, not a metadata key: metadata holds the reference's keys only
+        hist.fused = plan.fused  # K steps per pass where the lattice allows (tk_plan_fused_info)
+        hist.cross = plan.cross  # lattices with defects / 3-D: the cross scheme (tk_plan_cross_info)
         return hist
     finally:
         plan.close()
@@ -245,18 +250,17 @@ def run_wave_sim(
     ``G`` is a ``networkx`` graph (not mutated) or a :class:`LatticeSpec`.  The CFL check clamps an
     unstable ``dt`` and emits a :class:`RuntimeWarning`, exactly as the reference does.
     """
-    steps = int(steps)
-    if steps < 0:
-        steps = 0  # range(steps) in the reference simply does not iterate
+    steps_requested = steps  # metadata["steps"] is the requested value (physics.py:67)
+    steps = max(int(steps), 0)  # range(steps) in the reference simply does not iterate
     if path not in ("auto", "graph", "structured"):
         raise ValueError("path must be 'auto', 'graph' or 'structured'")
     if isinstance(G, LatticeSpec):
         return _run_lattice(G, steps, initial_data, c, dt, damping, device, record or "probes", probes, energy,
-                            dtype, max(int(snapshot_every), 1))
+                            dtype, max(int(snapshot_every), 1), steps_requested)
     if dtype != "float64":
         raise ValueError("dtype='float32' is available for LatticeSpec input only")
     return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes, energy,
-                      reorder)
+                      reorder, steps_requested)
 
 
 def run_fft(

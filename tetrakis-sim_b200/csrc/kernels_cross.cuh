@@ -42,6 +42,7 @@ struct FxDev {
     // partial sums of the participation-masked cross cells written by fx_cross_step_kernel
     int nsegR, nchR, rcR;   // row band: 32-cell segments per row, row chunks, rows per chunk
     int nsegC, nchC, rcC;   // column band: segments of cd_list, chunks of bulk rows, rows per chunk
+    int wshC;               // column band: log2 of the lanes per row (W = 2^wshC >= min(nC, 32) columns per warp)
     double *prowX;  // [L][nR][nsegR][4]
     double *pcolX;  // [L][nchR][S][4]
     double *prowC;  // [L][nbr][nsegC][4]
@@ -50,9 +51,11 @@ struct FxDev {
 
 // ---------------------------------------------------------------------------------------------------------
 // Cross stage, cells: one leapfrog step (MODE 0) or the sums only (MODE 1) of the cross cells.
-// A warp task = (layer, 32-cell segment, row chunk) of the ROW BAND (rows of R_d, all columns) or of the
-// COLUMN BAND (bulk rows, columns of C_d); one cell per lane (256-bit accesses), marching down the chunk's rows
-// like lat_step_kernel: column sums in registers, one transposing butterfly per row for the row sums.
+// A warp task = (layer, column segment, row chunk) of the ROW BAND (rows of R_d, all columns, 32 columns per warp)
+// or of the COLUMN BAND (bulk rows, columns of C_d).  One cell per lane (256-bit accesses); a warp covers W columns
+// x 32/W rows per iteration -- W = 32 in the row band, the smallest power of two >= |C_d| (at most 32) in the column
+// band, so a narrow C_d does not leave most lanes idle -- and marches down its chunk like lat_step_kernel: column
+// sums in registers, row sums by a butterfly over the W lanes of a row.
 // rowinfo / colinfo hold the TOTAL line sums of the state being read (fx_lines_kernel) + the static counts.
 template <int MODE>
 __global__ void __launch_bounds__(256, 2)
@@ -73,10 +76,12 @@ fx_cross_step_kernel(const __grid_constant__ LatDev P, const __grid_constant__ F
     const int seg = (int)(task % nseg), ch = (int)(task / nseg);
     const int rc = band ? X.rcC : X.rcR, nrows = band ? X.nbr : X.nR, nch = band ? X.nchC : X.nchR;
     const int ncolb = band ? X.nC : S;
+    const int wsh = band ? X.wshC : 5, W = 1 << wsh, rpw = 32 >> wsh;  // lanes per row, rows per iteration
     const int *__restrict__ rlist = band ? X.br_list : X.rd_list;
-    const int j = seg * 32 + lane;
-    const bool valid = j < ncolb;
-    const int c = band ? (valid ? X.cd_list[j] : 0) : j;
+    const int jl = lane & (W - 1), rs = lane >> wsh;
+    const int j = seg * W + jl;
+    const bool vcol = j < ncolb;
+    const int c = band ? (vcol ? X.cd_list[j] : 0) : min(j, S - 1);
 
     const size_t plane = (size_t)S * S * 4;
     const size_t zbase = (size_t)(zl + P.halo) * plane;
@@ -85,16 +90,23 @@ fx_cross_step_kernel(const __grid_constant__ LatDev P, const __grid_constant__ F
     const double degbase = 4.0 + (zm_on ? 1.0 : 0.0) + (zp_on ? 1.0 : 0.0);
 
     double CS[4] = {0, 0, 0, 0}, CC[4] = {0, 0, 0, 0}, cacc[4] = {0, 0, 0, 0};
-    if (STEP && valid) {
+    if (STEP && vcol) {
         ld256_nc(P.colinfo + ((size_t)zl * S + c) * 8, CS);
         ld256_nc(P.colinfo + ((size_t)zl * S + c) * 8 + 4, CC);
     }
     const int i_begin = ch * rc, i_end = min(nrows, i_begin + rc);
     const int tab0 = c / kTabSeg;
     double *__restrict__ prow = band ? X.prowC : X.prowX;
-    for (int i = i_begin; i < i_end; ++i) {
-        const int r = rlist[i];
+    for (int ib = i_begin; ib < i_end; ib += rpw) {
+        const int i = ib + rs;
+        const bool valid = vcol && i < i_end;
+        const int r = rlist[min(i, nrows - 1)];
         const size_t off = zbase + ((size_t)r * S + c) * 4;
+        if (STEP && valid && i + rpw < i_end && (jl & 3) == 0) {  // next iteration's rows towards L2, one request per 128 B
+            const size_t o2 = zbase + ((size_t)rlist[i + rpw] * S + c) * 4;
+            prefetch_l2(u + o2);
+            prefetch_l2(w + o2);
+        }
         double uq[4] = {0, 0, 0, 0}, upq[4] = {0, 0, 0, 0}, zm[4] = {0, 0, 0, 0}, zp[4] = {0, 0, 0, 0};
         int det = -1;
         if (valid) {
@@ -115,9 +127,11 @@ fx_cross_step_kernel(const __grid_constant__ LatDev P, const __grid_constant__ F
 #pragma unroll
             for (int q = 0; q < 4; ++q) pun[q] = ((f >> q) & 1u) ? uq[q] : 0.0;
         } else {
-            double RS[4], RC[4];
-            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8, RS);
-            ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8 + 4, RC);
+            double RS[4] = {0, 0, 0, 0}, RC[4] = {0, 0, 0, 0};
+            if (valid) {
+                ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8, RS);
+                ld256_nc(P.rowinfo + ((size_t)zl * S + r) * 8 + 4, RC);
+            }
             if (all_plain) {
                 const double cell = (uq[0] + uq[1]) + (uq[2] + uq[3]);
 #pragma unroll
@@ -146,9 +160,22 @@ fx_cross_step_kernel(const __grid_constant__ LatDev P, const __grid_constant__ F
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) cacc[q] += pun[q];
-        warp_sum4_store(pun, lane, prow + (((size_t)zl * nrows + i) * nseg + seg) * 4);
+        if (wsh == 5) {
+            if (i < i_end) warp_sum4_store(pun, lane, prow + (((size_t)zl * nrows + i) * nseg + seg) * 4);
+        } else {  // butterfly over the W lanes of each row; lane jl == 0 of a row stores its four sums
+            for (int o = W >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pun[q] += __shfl_xor_sync(0xffffffffu, pun[q], o);
+            }
+            if (jl == 0 && i < i_end) st256(prow + (((size_t)zl * nrows + i) * nseg + seg) * 4, pun);
+        }
     }
-    if (valid) st256((band ? X.pcolC : X.pcolX) + (((size_t)zl * nch + ch) * ncolb + j) * 4, cacc);
+    // column sums of the chunk: add the 32/W row lanes of a column (fixed tree), lanes of row 0 store
+    for (int o = 16; o >= W; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cacc[q] += __shfl_xor_sync(0xffffffffu, cacc[q], o);
+    }
+    if (vcol && rs == 0) st256((band ? X.pcolC : X.pcolX) + (((size_t)zl * nch + ch) * ncolb + j) * 4, cacc);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -163,7 +190,8 @@ struct FxLines {
     double coeff, damping;
     double *rowinfo, *colinfo;        // [L][S][8] total line sums (0-3) + static counts (4-7)
     double *Bcur[2], *Bprev[2];       // [kind][L][S][8] bulk parts (stride 8, entries 0-3), two time levels
-    double *ycur[2], *yprev[2];       // [kind][L][S][4] responses
+    double *ycur[2], *yprev[2];       // [kind] responses, [L][S][4][2]: the two time levels of a value are adjacent
+                                      // (the pointers differ by one double), so the bulk pass fetches both at once
     const double *tot_in;             // [2][L][nblk][4] per-block totals over bulk lines of the previous X
     double *tot_out;
     const void *state;                // probes
@@ -253,16 +281,16 @@ fx_lines_kernel(const __grid_constant__ FxDev X, const __grid_constant__ FxLines
                     const double *Yc = A.ycur[kind], *Yp = A.yprev[kind];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        yc[q] = Yc[li * 4 + q];
-                        yp[q] = A.first == 2 ? 0.0 : Yp[li * 4 + q];
-                        if (zl > 0) ys[q] += Yc[(li - S) * 4 + q];
-                        if (zl < L - 1) ys[q] += Yc[(li + S) * 4 + q];
+                        yc[q] = Yc[(li * 4 + q) * 2];
+                        yp[q] = A.first == 2 ? 0.0 : Yp[(li * 4 + q) * 2];
+                        if (zl > 0) ys[q] += Yc[((li - S) * 4 + q) * 2];
+                        if (zl < L - 1) ys[q] += Yc[((li + S) * 4 + q) * 2];
                     }
                 }
                 const double sy = (yc[0] + yc[1]) + (yc[2] + yc[3]);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                    A.yprev[kind][li * 4 + q] = caz * yc[q] + cb * yp[q] + A.coeff * ((sy + xp[q]) + ys[q]);
+                    A.yprev[kind][(li * 4 + q) * 2] = caz * yc[q] + cb * yp[q] + A.coeff * ((sy + xp[q]) + ys[q]);
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) Bn[q] = A.Bcur[kind][li * 8 + q];
@@ -372,86 +400,155 @@ __device__ __forceinline__ void fx_tick(FxPipe<K, UNDAMPED> &p, int t, int L, do
     outK1 = p.w[K - 1][SB];  // level K-1 at layer t-K (computed one tick ago)
 }
 
-__device__ __forceinline__ double hadamard4(double v, int lane)
+// Sum / difference modes of the four quadrant values held by lanes 4j..4j+3: two butterfly rounds; m1 / m2 are sign
+// masks for the high word (0x80000000 on odd lanes / on lanes with bit 1 set).  Applying it twice gives 4 x identity.
+__device__ __forceinline__ double fx_flip(double v, int m) { return __hiloint2double(__double2hiint(v) ^ m, __double2loint(v)); }
+__device__ __forceinline__ double hadamard4(double v, int m1, int m2)
 {
-    double t = __shfl_xor_sync(0xffffffffu, v, 1);
-    v = (lane & 1) ? t - v : v + t;
-    t = __shfl_xor_sync(0xffffffffu, v, 2);
-    v = (lane & 2) ? t - v : v + t;
+    v = __shfl_xor_sync(0xffffffffu, v, 1) + fx_flip(v, m1);
+    v = __shfl_xor_sync(0xffffffffu, v, 2) + fx_flip(v, m2);
     return v;
+}
+
+// Loads: every thread keeps a ring of PD ticks of its own inputs (u_t, u_{t-1} of layer t: 8 bytes each; the row and
+// the column response of layer t-K, both time levels: 16 bytes each) in shared memory, filled with cp.async copies PD
+// ticks ahead and completed with cp.async.wait_group -- a thread only ever reads what it copied itself, so there is no
+// block-level barrier and no register is spent on the prefetch depth (the K-level pipeline needs them all).
+constexpr int kFxPD = 6;                                    // ticks of loads in flight per thread
+constexpr int kFxSlotBytes = 256 * (8 + 8 + 16 + 16);       // one tick of one CTA
+
+template <int K, bool UNDAMPED>
+struct FxCtx {
+    FxPipe<K, UNDAMPED> p;
+    // kernel arguments (uniform) and per-thread running offsets: every address is base + offset
+    const double *in_a, *in_b, *yR, *yC;
+    double *out_a, *out_b;
+    size_t o;              // element offset of layer t of this thread's value (advances by `plane` per tick)
+    size_t ol;             // element offset of the row response pair of layer t (advances by `lstride2` per tick)
+    long long dcr;         // column response pair = row response pair + dcr
+    unsigned char *r8, *r16;  // this thread's 8-byte / 16-byte places inside slot 0 of the ring
+    double lam, cb, coeff;
+    size_t plane, lstride2;
+    int L, m1, m2;
+    bool act;
+};
+
+// One tick.  R6 = t mod 6 picks the ring slot and (mod 3) the rotation of the pipeline windows at compile time.
+// STEADY: K < t < L - PD, i.e. every stage is away from the end layers, the tick loads, requests and stores.
+template <int K, bool UNDAMPED, int R6, bool STEADY>
+__device__ __forceinline__ void fx_bulk_tick(FxCtx<K, UNDAMPED> &c, int t)
+{
+    cp_async_wait<kFxPD - 1>();
+    unsigned char *s8 = c.r8 + R6 * kFxSlotBytes, *s16 = c.r16 + R6 * kFxSlotBytes;
+    double na = *reinterpret_cast<const double *>(s8);
+    double nb = *reinterpret_cast<const double *>(s8 + 256 * 8);
+    const double2 yr = *reinterpret_cast<const double2 *>(s16);
+    const double2 yc = *reinterpret_cast<const double2 *>(s16 + 256 * 16);
+    if (!STEADY && t >= c.L) {
+        na = 0.0;
+        nb = 0.0;
+    }
+    // request the inputs of tick t + PD into the slot just read (same thread: program order)
+    if (STEADY || t + kFxPD < c.L) {
+        cp_async8(s8, c.in_a + c.o + kFxPD * c.plane);
+        cp_async8(s8 + 256 * 8, c.in_b + c.o + kFxPD * c.plane);
+    }
+    if (STEADY || (t + kFxPD >= K && t + kFxPD < c.L + K)) {  // responses of layer t + PD - K
+        const double *pr = c.yR + c.ol + (long long)(kFxPD - K) * (long long)c.lstride2;
+        cp_async16(s16, pr, true);
+        cp_async16(s16 + 256 * 16, pr + c.dcr, true);
+    }
+    cp_async_commit();
+    const double h0 = hadamard4(na, c.m1, c.m2), hm = hadamard4(nb, c.m1, c.m2);
+    double oK, oK1;
+    fx_tick<K, UNDAMPED, R6 % 3, !STEADY>(c.p, t, c.L, c.lam, c.cb, c.coeff, h0, hm, oK, oK1);
+    if (STEADY || t >= K) {
+        const double va = hadamard4(oK, c.m1, c.m2), vb = hadamard4(oK1, c.m1, c.m2);
+        if (c.act) {  // .x = level K, .y = level K-1 (the host starts a pass on the slot that makes it so)
+            c.out_a[c.o - K * c.plane] = fma(0.25, va, yr.x + yc.x);
+            c.out_b[c.o - K * c.plane] = fma(0.25, vb, yr.y + yc.y);
+        }
+    }
+    c.o += c.plane;
+    c.ol += c.lstride2;
 }
 
 template <int K, bool UNDAMPED, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 fx_bulk3d_kernel(const __grid_constant__ FxDev X, int halo, const double *in_a, const double *in_b, double *out_a,
-                 double *out_b, const double *__restrict__ yRa, const double *__restrict__ yRb,
-                 const double *__restrict__ yCa, const double *__restrict__ yCb, double ca, double cb, double coeff,
-                 int nct, int pf_layers)
+                 double *out_b, const double *__restrict__ yR, const double *__restrict__ yC, double ca, double cb,
+                 double coeff, int nct)
 {
+    extern __shared__ __align__(16) unsigned char tk_smem[];
     const int S = X.S, L = X.L;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ct = blockIdx.x % nct;
     const int bi = blockIdx.x / nct;
     const int r = X.br_list[bi];  // bulk rows only
     const int c = ct * 64 + warp * 8 + (lane >> 2), m = lane & 3;
-    const bool act = c < S && !X.colflag[min(c, S - 1)];
+    const int cc = min(c, S - 1);  // lanes beyond the row / on cross columns compute on valid memory and store nothing
+    FxCtx<K, UNDAMPED> x;
+    x.act = c < S && !X.colflag[cc];
     // a warp whose 8 cells are all cross cells / beyond the row has nothing to do (no block-level sync below)
-    if (!__any_sync(0xffffffffu, act)) return;
-    const size_t plane = (size_t)S * S * 4;
-    const size_t cell0 = (size_t)halo * plane + ((size_t)r * S + min(c, S - 1)) * 4 + m;
-    const double lam = m == 0 ? ca + 4.0 * coeff : ca;
-    FxPipe<K, UNDAMPED> p;
+    if (!__any_sync(0xffffffffu, x.act)) return;
+    x.in_a = in_a; x.in_b = in_b; x.out_a = out_a; x.out_b = out_b; x.yR = yR; x.yC = yC;
+    x.plane = (size_t)S * S * 4;
+    x.lstride2 = (size_t)S * 8;
+    x.L = L;
+    x.o = (size_t)halo * x.plane + ((size_t)r * S + cc) * 4 + m;
+    x.ol = ((size_t)r * 4 + m) * 2;
+    x.dcr = (yC - yR) + ((long long)cc - r) * 8;
+    x.r8 = tk_smem + threadIdx.x * 8;
+    x.r16 = tk_smem + 256 * 16 + threadIdx.x * 16;
+    x.lam = m == 0 ? ca + 4.0 * coeff : ca;
+    x.cb = cb;
+    x.coeff = coeff;
+    x.m1 = (lane & 1) ? (int)0x80000000 : 0;
+    x.m2 = (lane & 2) ? (int)0x80000000 : 0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) p.w[k][0] = p.w[k][1] = p.w[k][2] = 0.0;
-    p.mprev = p.mcur = 0.0;
-    const bool pf_lane = pf_layers > 0 && act && (lane & 15) == 0;  // one request per 128-byte line
-    const int nt = L + K;
-    // software pipeline of the loads: the values of tick t+1 are requested before tick t is computed
-    double na = 0.0, nb = 0.0;
-    if (act) {
-        na = in_a[cell0];
-        nb = in_b[cell0];
+    for (int k = 0; k < K; ++k) x.p.w[k][0] = x.p.w[k][1] = x.p.w[k][2] = 0.0;
+    x.p.mprev = x.p.mcur = 0.0;
+    // prime the ring: ticks 0 .. PD-1
+#pragma unroll
+    for (int d = 0; d < kFxPD; ++d) {
+        if (d < L) {
+            cp_async8(x.r8 + d * kFxSlotBytes, in_a + x.o + d * x.plane);
+            cp_async8(x.r8 + d * kFxSlotBytes + 256 * 8, in_b + x.o + d * x.plane);
+        }
+        if (d >= K && d < L + K) {
+            const double *pr = yR + x.ol + (long long)(d - K) * (long long)x.lstride2;
+            cp_async16(x.r16 + d * kFxSlotBytes, pr, true);
+            cp_async16(x.r16 + d * kFxSlotBytes + 256 * 16, pr + x.dcr, true);
+        }
+        cp_async_commit();
     }
-    if (pf_lane)
-        for (int z = 1; z < min(L, 1 + pf_layers); ++z) {
-            prefetch_l2(in_a + cell0 + (size_t)z * plane);
-            prefetch_l2(in_b + cell0 + (size_t)z * plane);
-        }
-    auto tick = [&](auto rot, int t) {
-        constexpr int R = decltype(rot)::value;
-        if (t >= nt) return;
-        // Hadamard modes of the layer loaded for this tick
-        const double h0 = hadamard4(na, lane), hm = hadamard4(nb, lane);
-        if (t + 1 < L && act) {
-            na = in_a[cell0 + (size_t)(t + 1) * plane];
-            nb = in_b[cell0 + (size_t)(t + 1) * plane];
-        } else {
-            na = 0.0;
-            nb = 0.0;
-        }
-        if (pf_lane && t + 1 + pf_layers < L) {
-            prefetch_l2(in_a + cell0 + (size_t)(t + 1 + pf_layers) * plane);
-            prefetch_l2(in_b + cell0 + (size_t)(t + 1 + pf_layers) * plane);
-        }
-        double oK, oK1;
-        if (t > K && t < L) fx_tick<K, UNDAMPED, R, false>(p, t, L, lam, cb, coeff, h0, hm, oK, oK1);
-        else fx_tick<K, UNDAMPED, R, true>(p, t, L, lam, cb, coeff, h0, hm, oK, oK1);
-        const int z = t - K;
-        if (z >= 0) {
-            const double va = 0.25 * hadamard4(oK, lane), vb = 0.25 * hadamard4(oK1, lane);
-            if (act) {
-                const size_t lr = ((size_t)z * S + r) * 4 + m, lc = ((size_t)z * S + c) * 4 + m;
-                out_a[cell0 + (size_t)z * plane] = va + (yRa[lr] + yCa[lc]);
-                out_b[cell0 + (size_t)z * plane] = vb + (yRb[lr] + yCb[lc]);
-            }
+    const int nt = L + K;
+    auto guarded = [&](int t) {  // any tick, rotation picked at run time
+        switch (t % 6) {
+        case 0: fx_bulk_tick<K, UNDAMPED, 0, false>(x, t); break;
+        case 1: fx_bulk_tick<K, UNDAMPED, 1, false>(x, t); break;
+        case 2: fx_bulk_tick<K, UNDAMPED, 2, false>(x, t); break;
+        case 3: fx_bulk_tick<K, UNDAMPED, 3, false>(x, t); break;
+        case 4: fx_bulk_tick<K, UNDAMPED, 4, false>(x, t); break;
+        default: fx_bulk_tick<K, UNDAMPED, 5, false>(x, t); break;
         }
     };
+    int t = 0;
+    const int t_steady = (K + 1 + 5) / 6 * 6;  // first multiple of 6 above K
 #pragma unroll 1
-    for (int t = 0; t < nt; t += 3) {
-        tick(std::integral_constant<int, 0>{}, t);
-        tick(std::integral_constant<int, 1>{}, t + 1);
-        tick(std::integral_constant<int, 2>{}, t + 2);
+    for (; t < min(nt, t_steady); ++t) guarded(t);
+#pragma unroll 1
+    for (; t + 6 <= L - kFxPD; t += 6) {
+        fx_bulk_tick<K, UNDAMPED, 0, true>(x, t);
+        fx_bulk_tick<K, UNDAMPED, 1, true>(x, t + 1);
+        fx_bulk_tick<K, UNDAMPED, 2, true>(x, t + 2);
+        fx_bulk_tick<K, UNDAMPED, 3, true>(x, t + 3);
+        fx_bulk_tick<K, UNDAMPED, 4, true>(x, t + 4);
+        fx_bulk_tick<K, UNDAMPED, 5, true>(x, t + 5);
     }
+#pragma unroll 1
+    for (; t < nt; ++t) guarded(t);
+    cp_async_wait<0>();
 }
 
 }  // namespace tk

@@ -265,7 +265,7 @@ lat_tables_kernel(int S, int nrows, int K, double coeff, double damping, double 
 //   CROSS (sheets with defects, kernels_cross.cuh): cells of the cross -- rows with rowflag, columns with colflag --
 //   are left alone (the cross stage has already advanced them in place) and do not enter the partial sums, which
 //   then are the BULK parts of the line sums; the responses come from fx_lines_kernel as two plain [line][4] arrays
-//   (respR = y_K, respC = y_K of the columns, respRb / respCb = y_{K-1}); ua / ub are the buffers u_t / u_{t-1} are
+//   (respR = y_K, respC = y_K of the columns, respRb / respCb = y_{K-1}; element stride 2); ua / ub are the buffers u_t / u_{t-1} are
 //   read from, oa / ob the ones u_{t+K} / u_{t+K-1} are written to (the same two, swapped when K is odd); probes are
 //   cross cells, so the probe path is off.
 template <int MINB, bool UNDAMPED, typename T = double, bool CROSS = false>
@@ -296,13 +296,13 @@ lat_fused2d_kernel(int S, int nrows, int K, T *ua, T *ub, const double *__restri
         const int cl_ = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
         const int c = col0 + cl_;
         double v;
-        if (CROSS) v = c < S ? (j < 4 ? respC : respCb)[(size_t)c * 4 + q] : 0.0;
+        if (CROSS) v = c < S ? (j < 4 ? respC : respCb)[((size_t)c * 4 + q) * 2] : 0.0;  // levels interleaved
         else v = (c < S && k >= 0) ? respC[((size_t)k * S + c) * 4 + q] : 0.0;
         colresp[((size_t)(j >> 1) * ncol + cl_) * 2 + (j & 1)] = v;
     }
     for (int i = threadIdx.x; i < (r_end - r_begin) * 8; i += blockDim.x) {
         const int rl = i >> 3, j = i & 7, q = j & 3, k = j < 4 ? K - 1 : K - 2;
-        if (CROSS) rowresp[i] = (j < 4 ? respR : respRb)[(size_t)(r_begin + rl) * 4 + q];
+        if (CROSS) rowresp[i] = (j < 4 ? respR : respRb)[((size_t)(r_begin + rl) * 4 + q) * 2];
         else rowresp[i] = k >= 0 ? respR[((size_t)k * nrows + r_begin + rl) * 4 + q] : 0.0;
     }
     __syncthreads();

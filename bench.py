@@ -14,8 +14,13 @@ Workloads (config.workload):
                     the cfg3 slab run of the same launch reported under "sharded_3d")
   cfg3-slab-1024x64 BASELINE configs[2] shape: 3-D 1024x1024, 64 layers PER GPU, black hole r=64 at the
                     global centre, layer slabs + halo push over NVLink peer memory (or NCCL)
-  cfg4-3d-512       BASELINE configs[3]: 3-D 512^3 singularity, mass 2000, pruned edges
+  cfg4-3d-512       BASELINE configs[3]: 3-D 512^3 singularity, mass 2000, pruned edges (K-step passes with the
+                    cross scheme of kernels_cross.cuh; TK_LAT_FUSE=0: one step per launch)
   cfg5-ensemble     BASELINE configs[4]: 65 536 independent 13x13x7 simulations
+  cfg1-batch        BASELINE configs[0]: tetrakis-batch --dim 3 --size 11 --layers 7 --radius 2.5 --steps 50 through
+                    the drop-in run_wave_sim(G) on the networkx graph, next to the literal CPU restatement (1 core)
+The default N=1 line (cfg2) also carries "sharded_3d" (the cfg3 slab through the multi-GPU slab code with no
+neighbours: the N=1 point of the 3-D weak-scaling series) and "other_configs" (cfg4, cfg3 fused, cfg5, cfg1).
   ell-tetrakis-64x16 / ell-grid-256   the generic sliced-ELL graph kernel on an explicit CSR (44 + 4w bytes/update)
 Prints ONE JSON line (rank 0).  `value` is device-timed with the state resident in HBM; `e2e` is the same
 metric through the C ABI with host buffers (kicks H2D, probe series + final state D2H inside the timed
@@ -53,11 +58,15 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+def ncu_traffic(workload, k=0):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), or None.
+    A capture of a K-step pass kernel only counts for a run with the same K."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return float(json.load(f)[workload]["bytes"])
+            e = json.load(f)[workload]
+        if k and int(e.get("steps_per_pass", k)) != int(k):
+            return None
+        return float(e["bytes"])
     except Exception:
         return None
 
@@ -146,7 +155,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's C/OpenMP clique-sum restatement on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------------
-def cpu_run(workload: str, steps: int, warmup: int, budget_s: float):
+def cpu_run(workload: str, steps: int, warmup: int, budget_s: float = 0.0):
+    """The oracle's C/OpenMP clique-sum restatement on a FIXED bounded sample of the workload: 2-D 4096^2 for the
+    sheet workloads, 3-D 512 x 512 x 16 for the 3-D ones (no defect), all host threads."""
     from oracle import wave_oracle as wo
 
     cores = os.cpu_count() or 1
@@ -158,13 +169,10 @@ def cpu_run(workload: str, steps: int, warmup: int, budget_s: float):
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
     except OSError:
         pass
-    three_d = workload.startswith("cfg3")
+    three_d = workload.startswith("cfg3") or workload.startswith("cfg4")
+    S, L = (512, 16) if three_d else (4096, 1)
 
-    def shape(size):
-        return (size, 16) if three_d else (size, 1)
-
-    def one(size, nsteps):
-        S, L = shape(size)
+    def one(nsteps):
         u0 = np.zeros(L * S * S * 4)
         u0[((L // 2 * S + S // 2) * S + S // 2) * 4] = 1.0
         maxdeg = 3 + 2 * (S - 1) + (2 if L > 1 else 0)
@@ -173,28 +181,45 @@ def cpu_run(workload: str, steps: int, warmup: int, budget_s: float):
         wo.run_structured(S, L, None, None, None, [], u0, nsteps, coeff, 0.0)
         return time.perf_counter() - t0, L * S * S * 4
 
-    t, n = one(256, 4)  # calibrate seconds per node-update
-    per_nu = max(t / (4 * n), 1e-12)
-    size = 256
-    for cand in ((128, 256, 512, 1024) if three_d else (512, 1024, 2048, 4096)):
-        S, L = shape(cand)
-        if (steps + warmup) * L * cand * cand * 4 * per_nu <= budget_s:
-            size = cand
     if warmup:
-        one(size, warmup)
-    t, n = one(size, steps)
-    S, L = shape(size)
+        one(warmup)
+    t, n = one(steps)
     sample = (f"{'3-D' if three_d else '2-D'} tetrakis {S}x{S}" + (f"x{L}" if three_d else "") +
-              f" no defect, {steps} steps, oracle/wave_oracle.c clique-sum restatement, OpenMP {cores} threads")
+              f" no defect (fixed sample), {steps} steps, oracle/wave_oracle.c clique-sum restatement, OpenMP {cores} threads")
     return {"value": n * steps / t / 1e9, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
             "seconds": t, "ms_per_step": 1e3 * t / max(steps, 1)}
+
+
+def cpu_literal_cfg1(steps: int = 50):
+    """BASELINE configs[0] on one host core with the LITERAL restatement of physics.py:106-129 (per-node neighbour
+    loops over the adjacency lists, oracle/wave_oracle.c:run_graph) -- what the reference's arithmetic costs once
+    the Python interpreter is taken out; the reference itself (Python over networkx) measured 0.59 s for the same
+    run on this image's host."""
+    from oracle import lattice_oracle as lo
+    from oracle import wave_oracle as wo
+
+    G, removed, center = lo.build_case(11, 3, 7, "blackhole", radius=2.5)
+    kick = lo.pick_kick_node(G, center, 3)
+    nodes, rowptr, colidx, inv_mass, potential = lo.graph_arrays(G)
+    deg = np.array([G.degree[n] for n in nodes], dtype=np.float64)
+    u0 = np.zeros(len(nodes))
+    u0[nodes.index(kick)] = 1.0
+    dt_eff, _, _ = wo.cfl_clamp(int(deg.max()), 1.0, 0.2, steps, 0.0)
+    wo.run_graph(rowptr, colidx, deg, inv_mass, potential, u0, 2, dt_eff ** 2, 0.0)
+    best = 1e9
+    for _ in range(5):
+        t0 = time.perf_counter()
+        wo.run_graph(rowptr, colidx, deg, inv_mass, potential, u0, steps, dt_eff ** 2, 0.0)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": len(nodes) * steps / best / 1e9, "unit": UNIT, "cores": 1, "kind": "port", "seconds": best,
+            "sample": f"cfg1 whole (3 064 nodes, {int(rowptr[-1]) // 2} edges, {steps} steps), literal per-edge loop in C, 1 core"}
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return 0
     workload = args.workload or ("cfg2-2d-8192" if args.gpus == 1 else "cfg2-sharded")
-    res = cpu_run(workload, args.steps, args.warmup, budget_s=150.0)
+    res = cpu_run(workload, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -218,19 +243,31 @@ def pinned_empty(n):
     return t, t.numpy()
 
 
-def gpu_single(args, dist=None, emit=True):
-    """One lattice per GPU.  N = 1: the bench line.  N > 1 (``dist`` given): N independent replicas of the same
-    sheet, one per rank -- a 2-D sheet does not shard (SURVEY.md 8e: "replicas only"), so there is no data-path
-    collective; the timed region is bracketed by barriers and the slowest rank's device time counts."""
+WORKLOADS = {
+    "cfg2-2d-8192": dict(dim=2, size=8192, layers=1, kw={}, dt=0.1,
+                         desc="2-D tetrakis {S}x{S}, no defect, fp64, kick (S/2,S/2,'A'), dt 0.1 -> CFL-clamped"),
+    "cfg3-slab-1024x64": dict(dim=3, size=1024, layers=64, kw=dict(defect="blackhole", radius=64.0), dt=0.1,
+                              desc="3-D tetrakis {S}x{S}x{L}, black hole r=64 at the centre, fp64"),
+    "cfg4-3d-512": dict(dim=3, size=512, layers=512,
+                        kw=dict(defect="singularity", radius=2.5, mass=2000.0, prune_edges=True), dt=0.1,
+                        desc="3-D tetrakis {S}x{S}x{L} singularity mass 2000 + prune_edges, fp64"),
+}
+
+
+def bench_lattice(workload, args, local=0, dist=None, steps=None, warmup=None, size=None, layers=None, fuse=True,
+                  clk=None, want_e2e=True):
+    """One lattice on one GPU through the C ABI (tk_plan_run).  The timed region -- `steps` steps, synchronised on
+    both sides -- is repeated until >= 50 ms and >= 5 repeats have been seen (the state stays resident and the
+    simulation simply continues); the reported time is the MEDIAN.  Returns the fields of a bench line."""
     import torch
 
     import tetrakis_sim_b200 as tk
+    from tetrakis_sim_b200 import _lib
 
-    rank = int(os.environ.get("RANK", "0")) if dist else 0
+    w = WORKLOADS[workload]
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     world = int(os.environ.get("WORLD_SIZE", "1")) if dist else 1
-    local = int(os.environ.get("LOCAL_RANK", str(rank))) if dist else 0
-    torch.cuda.init()
-    torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
 
     def fence():
@@ -245,21 +282,8 @@ def gpu_single(args, dist=None, emit=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    workload = args.workload or "cfg2-2d-8192"
-    if workload == "cfg2-2d-8192":
-        spec = tk.LatticeSpec(size=args.size or 8192, dim=2)
-        dt_req, desc = 0.1, "2-D tetrakis {0}x{0}, no defect, fp64, kick (S/2,S/2,'A'), dt 0.1 -> CFL-clamped"
-    elif workload == "cfg3-slab-1024x64":
-        spec = tk.LatticeSpec(size=args.size or 1024, dim=3, layers=args.layers or 64, defect="blackhole",
-                              radius=64.0)
-        dt_req, desc = 0.1, "3-D tetrakis {0}x{0}x" + str(spec.layers) + ", black hole r=64 at the centre, fp64"
-    elif workload == "cfg4-3d-512":
-        spec = tk.LatticeSpec(size=args.size or 512, dim=3, layers=args.layers or 512, defect="singularity",
-                              radius=2.5, mass=2000.0, prune_edges=True)
-        dt_req, desc = 0.1, "3-D tetrakis {0}^3 singularity mass 2000 + prune_edges, fp64"
-    else:
-        raise SystemExit(f"unknown workload {workload}")
-    desc = desc.format(spec.size)
+    spec = tk.LatticeSpec(size=size or w["size"], dim=w["dim"], layers=layers or w["layers"], **w["kw"])
+    desc = w["desc"].format(S=spec.size, L=spec.layers)
     kick = spec.kick_node() if spec.defect != "none" else spec.bench_kick_node()
     f32 = args.dtype == "f32"
     bpu = BYTES_PER_UPDATE / 2 if f32 else BYTES_PER_UPDATE
@@ -268,96 +292,282 @@ def gpu_single(args, dist=None, emit=True):
     maxdeg = plan.max_degree
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build  # graph-to-device compile (excluded from every rate below)
-    limit = 1.0 / np.sqrt(maxdeg)
-    dt_eff = min(dt_req, limit)
+    dt_eff = min(w["dt"], 1.0 / np.sqrt(maxdeg))
     coeff = dt_eff ** 2
     n_updates = spec.num_nodes  # surviving nodes
     kidx = [spec.index(kick)]
 
-    clk = ClockSampler(local).start()
     plan.set_state_sparse(kidx, [1.0])
-    plan.run(args.warmup, coeff, 0.0, probes=kidx)
+    plan.run(warmup, coeff, 0.0, probes=kidx, fuse=fuse)
     fence()
-    l0 = plan.launches
-    with clk:
+    reps = []
+    if clk is not None:
+        clk.mark_begin()
+    while len(reps) < 5 or (sum(r[0] for r in reps) < 50.0 and len(reps) < 40):
+        l0 = plan.launches
         fence()
-        out = plan.run(args.steps, coeff, 0.0, probes=kidx, timed=True, kernel_timing=True)
+        out = plan.run(steps, coeff, 0.0, probes=kidx, timed=True, kernel_timing=True, fuse=fuse)
         fence()
-    launches = plan.launches - l0
-    ms = max_over_ranks(out["elapsed_ms"])  # device time (CUDA events on the plan's stream), slowest rank
-    kms = out["step_kernel_ms"]
-    value = world * n_updates * args.steps / (ms * 1e-3) / 1e9
+        reps.append((max_over_ranks(out["elapsed_ms"]), out["step_kernel_ms"], plan.launches - l0))
+    if clk is not None:
+        clk.mark_end()
+    order = sorted(range(len(reps)), key=lambda i: reps[i][0])
+    ms, kms, launches = reps[order[len(reps) // 2]]  # the median repeat (its own kernel time and launch count)
+    steps_done = warmup + steps * len(reps)
+    value = world * n_updates * steps / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
-    # Defect-free 2-D sheets advance K steps per pass (kernels_fused.cuh): a pass reads u_t, u_{t-1} and
-    # writes u_{t+K}, u_{t+K-1} = 32 B per node per pass; the remaining steps (steps mod K) move 24 B each.
-    fused = plan.fused
-    fk = fused["steps_per_pass"]
-    npass = -(-fused["fused_steps"] // fk) if fk else 0
-    nsingle = args.steps - fused["fused_steps"]
-    alg_bytes = n_updates * (npass * (4 * bpu / 3) + nsingle * bpu)
-    achieved = alg_bytes / (kms * 1e-3) / 1e9
-    kernel_launches = npass + nsingle
-    checksum = float(plan.get_state().sum()) if spec.num_slots <= 600_000_000 else None
 
-    # e2e: the whole run through the C ABI with host buffers (kicks H2D; probe series and the final
-    # state D2H into pinned host memory), device-synchronised wall clock
-    hold, final = pinned_empty(plan.num_nodes)
-    from tetrakis_sim_b200 import _lib
-    fence()
-    t0 = time.perf_counter()
-    plan.set_state_sparse(kidx, [1.0])
-    o2 = plan.run(args.steps, coeff, 0.0, probes=kidx)
-    _lib.check(_lib.lib().tk_plan_get_state(plan._h, _lib._p(final), None))
-    fence()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = {"value": world * n_updates * args.steps / e2e_s / 1e9, "unit": UNIT,
-           "h2d_bytes_per_step": world * 16.0 / args.steps,
-           "d2h_bytes_per_step": world * (final.nbytes + o2["probes"].nbytes) / args.steps,
-           "seconds": e2e_s, "includes": "set_state_sparse + run + probe series D2H + final state D2H (pinned)"}
+    # ---- the dominant kernel and its algorithmic bytes
+    fused, cross = plan.fused, plan.cross
+    fk = fused["steps_per_pass"]
+    nsingle = steps - fused["fused_steps"]
+    slots = spec.num_slots
+    if cross["steps_per_pass"]:
+        # cross scheme (kernels_cross.cuh): a bulk pass reads u_t, u_{t-1} and writes u_{t+K}, u_{t+K-1} of the BULK nodes
+        bulk = slots * (1.0 - cross["cross_fraction"])
+        npass = fused["fused_steps"] // fk + (1 if fused["fused_steps"] % fk else 0)
+        pass_bytes = 4 * (bpu / 3) * bulk
+        alg_bytes = npass * pass_bytes + nsingle * bpu * n_updates
+        kernel = (f"fx_bulk3d_kernel<{fk}>" if spec.dim == 3 else f"lat_fused2d_kernel<CROSS> (K={fk})") + \
+                 " (the bulk pass of the cross scheme)"
+        cross_bytes = fused["fused_steps"] * bpu * slots * cross["cross_fraction"]
+        extra = {"cross_stage": {"rows": cross["cross_rows"], "cols": cross["cross_cols"],
+                                 "fraction_of_lattice": cross["cross_fraction"],
+                                 "algorithmic_bytes": cross_bytes,
+                                 "note": "the cross cells and every line sum are stepped one step at a time "
+                                         "(fx_cross_step_kernel + fx_lines_kernel, 2 launches per step); their time is "
+                                         "the part of the step outside kernel_share_of_step"},
+                 "bytes_per_update_all_kernels": (alg_bytes + cross_bytes) / (n_updates * steps)}
+        traffic_key = workload + "-fused"
+    elif fk:
+        npass = -(-fused["fused_steps"] // fk)
+        pass_bytes = 4 * (bpu / 3) * n_updates
+        alg_bytes = npass * pass_bytes + nsingle * bpu * n_updates
+        kernel = f"lat_fused2d_kernel{'<float>' if f32 else ''} (K={fk})"
+        extra, traffic_key = {}, workload + "-fused"
+    else:
+        npass, pass_bytes = 0, bpu * n_updates
+        alg_bytes = nsingle * bpu * n_updates
+        kernel = "lat_step_f32_kernel" if f32 else "lat_step_kernel"
+        extra, traffic_key = {}, workload
+    kernel_launches = npass + nsingle
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = None if f32 else ncu_traffic(traffic_key, fk)
+    checksum = float(plan.get_state().sum()) if slots <= 600_000_000 else None
+
+    e2e = None
+    if want_e2e:
+        # e2e through the C ABI with host buffers, device-synchronised wall clock: kick H2D, `steps` steps, the probe
+        # series D2H and its |DFT| + dominant bin (what tetrakis-batch writes out); "with_final_state" adds the D2H
+        # of the whole final state into pinned host memory (what run_wave_sim's history.final_state holds)
+        hold, final = pinned_empty(plan.num_nodes)
+        fence()
+        t0 = time.perf_counter()
+        plan.set_state_sparse(kidx, [1.0])
+        o2 = plan.run(steps, coeff, 0.0, probes=kidx, fuse=fuse)
+        spectrum, dom = tk.dft_abs(o2["probes"][:, 0], device=local)
+        fence()
+        t1 = time.perf_counter()
+        _lib.check(_lib.lib().tk_plan_get_state(plan._h, _lib._p(final), None))
+        fence()
+        t2 = time.perf_counter()
+        e_probe, e_full = max_over_ranks(t1 - t0), max_over_ranks(t2 - t0)
+        e2e = {"value": world * n_updates * steps / e_probe / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": world * (16.0 + o2["probes"].nbytes) / steps,
+               "d2h_bytes_per_step": world * (o2["probes"].nbytes + spectrum.nbytes + 8) / steps,
+               "seconds": e_probe,
+               "includes": "set_state_sparse (kick H2D) + run + probe series D2H + probe series H2D, |DFT| and "
+                           "dominant bin D2H (tk_dft_abs)",
+               "with_final_state": {"value": world * n_updates * steps / e_full / 1e9, "seconds": e_full,
+                                    "d2h_bytes_per_step": world * (final.nbytes + o2["probes"].nbytes) / steps,
+                                    "includes": "the above + the whole final state D2H into pinned host memory"}}
     tiling = plan.tiling
     if fk:
-        tiling = {"steps_per_pass": fk, "cells_per_lane": 1, "segs_per_cta": tiling["segs_per_cta"],
-                  "rows_per_cta": fused["rows_per_cta"], "ctas_per_sm": fused["ctas_per_sm"],
-                  "single_steps": nsingle,
-                  "temporal_blocking": (f"{npass} passes of <= {fk} steps: every node update is computed (cell-local, in "
-                                        "registers), the intermediate states are not stored; the row/column sums of the "
-                                        "intermediate steps follow from closed recurrences because the sheet has no "
-                                        "defect.  TK_LAT_FUSE=0 runs one step per launch (24 B per update).")}
+        tiling = {"steps_per_pass": fk, "single_steps": nsingle, "passes": npass,
+                  "temporal_blocking": ("every node update is computed, the intermediate states are not stored; " +
+                                        ("cross scheme: the rows / columns of the defect and of the probe are stepped "
+                                         "explicitly with every line sum, the bulk takes one pass per K steps"
+                                         if cross["steps_per_pass"] else
+                                         "the row/column sums of the intermediate steps follow from closed recurrences "
+                                         "because the sheet has no defect") +
+                                        ".  TK_LAT_FUSE=0 runs one step per launch (24 B per update).")}
+        if not cross["steps_per_pass"]:
+            tiling.update(rows_per_cta=fused["rows_per_cta"], ctas_per_sm=fused["ctas_per_sm"])
     plan.close()
-
-    cpu = None
-    if not args.no_cpu and world == 1:
-        cpu = cpu_run(workload, steps=100, warmup=2, budget_s=40.0)  # ~10 s of CPU work
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": workload, "lattice": desc.replace("fp64", "fp32 state (fp64 sums)") if f32 else desc, "nodes": n_updates, "max_degree": maxdeg,
-                   "effective_dt": dt_eff, "kick": list(map(str, kick)),
-                   "l2": f"state {2 * spec.num_slots * 8 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
-                   "tiling": tiling, "plan_build_s": t_build,
-                   "parallelism": "single GPU" if world == 1 else
-                   f"{world} independent replicas of the sheet, one per GPU, no data-path collective (a 2-D sheet "
-                   "does not shard; the sharded 3-D slab run of the same launch is reported under sharded_3d)"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
-                     "traffic": None if f32 else ncu_traffic(workload + ("-fused" if fk else "")),
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes / kernel_launches,
-                     "kernel": (f"lat_fused2d_kernel{'<float>' if f32 else ''} (K={fk})" if fk
-                                else ("lat_step_f32_kernel" if f32 else "lat_step_kernel")),
-                     "bytes_per_update": alg_bytes / (n_updates * args.steps),
-                     "kernel_ms_per_launch": kms / kernel_launches,
-                     "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0},
-        "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
+    return {
+        "value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+        "timing": {"repeats": len(reps), "median_ms": ms, "min_ms": reps[order[0]][0], "max_ms": reps[order[-1]][0],
+                   "rule": "the steps-step region repeated until >= 50 ms and >= 5 repeats; value from the median"},
+        "config": {"workload": workload, "lattice": desc.replace("fp64", "fp32 state (fp64 sums)") if f32 else desc,
+                   "nodes": n_updates, "max_degree": maxdeg, "effective_dt": dt_eff, "kick": list(map(str, kick)),
+                   "l2": f"state {2 * slots * (4 if f32 else 8) / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
+                   "tiling": tiling, "plan_build_s": t_build},
+        "roofline": dict({"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                          "traffic": traffic, "peak_source": peak_src,
+                          "algorithmic_bytes_per_launch": alg_bytes / max(kernel_launches, 1), "kernel": kernel,
+                          "bytes_per_update": alg_bytes / (n_updates * steps),
+                          "kernel_ms_per_launch": kms / max(kernel_launches, 1),
+                          "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0}, **extra),
+        "e2e": e2e, "gpu_launches": launches,
         # sum_i u_t(i) = 1 + t for unit masses (zero column sums of the Laplacian): a whole-lattice checksum
         "checksum_sum_u": checksum,
-        "checksum_expected": float(args.warmup + args.steps + 1) if spec.defect != "singularity" else None,
+        "checksum_expected": float(steps_done + 1) if spec.defect != "singularity" else None,
     }
+
+
+def gpu_single(args, dist=None, emit=True):
+    """One lattice per GPU.  N = 1: the bench line.  N > 1 (``dist`` given): N independent replicas of the same
+    sheet, one per rank -- a 2-D sheet does not shard (SURVEY.md 8e: "replicas only"), so there is no data-path
+    collective; the timed region is bracketed by barriers and the slowest rank's device time counts."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0")) if dist else 0
+    world = int(os.environ.get("WORLD_SIZE", "1")) if dist else 1
+    local = int(os.environ.get("LOCAL_RANK", str(rank))) if dist else 0
+    torch.cuda.init()
+    torch.cuda.set_device(local)
+    workload = args.workload or "cfg2-2d-8192"
+    if workload not in WORKLOADS:
+        raise SystemExit(f"unknown workload {workload}")
+    clk = ClockSampler(local).start()
+    res = bench_lattice(workload, args, local=local, dist=dist, size=args.size, layers=args.layers, clk=clk)
+    clk.__exit__()
+    res["config"]["parallelism"] = ("single GPU" if world == 1 else
+                                    f"{world} independent replicas of the sheet, one per GPU, no data-path collective")
+    cpu = None
+    if not args.no_cpu and world == 1:
+        cpu = cpu_run(workload, steps=100 if workload.startswith("cfg2") else 20, warmup=2)  # ~10 s of CPU work
+    line = {
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": res["config"],
+        "roofline": res["roofline"],
+        "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clk.summary(), "timing": res["timing"],
+        "checksum_sum_u": res["checksum_sum_u"], "checksum_expected": res["checksum_expected"],
+    }
+    if world == 1 and args.workload is None and not args.no_extras:
+        line.update(default_extras(args, local))
     if emit and rank == 0:
         print(json.dumps(line))
     return line
+
+
+def default_extras(args, local):
+    """What the default N=1 line carries besides cfg2: the N=1 point of the 3-D weak-scaling series (the cfg3 slab
+    through the multi-GPU slab code, no neighbours), and short lines of the other BASELINE configs."""
+    import argparse as _ap
+
+    from tetrakis_sim_b200.slab import bench_slabs
+
+    out = {}
+    a3 = _ap.Namespace(**vars(args))
+    a3.workload, a3.size, a3.layers = "cfg3-slab-1024x64", None, None
+    slab = bench_slabs(a3, emit=False)
+    out["sharded_3d"] = {k: slab[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches",
+                                              "timing", "checksum_sum_u", "checksum_expected")}
+    out["sharded_3d"]["note"] = ("N=1 point of the weak-scaling series of bench.py --gpus N: the same SlabRunner code, one "
+                                 "step per launch, no neighbours.  The K-step passes of the same lattice on one GPU "
+                                 "are under other_configs.")
+    other = {}
+    a = _ap.Namespace(**vars(args))
+    a.dtype = "f64"
+    for wl, st in (("cfg4-3d-512", 64), ("cfg3-slab-1024x64", 64)):
+        r = bench_lattice(wl, a, local=local, steps=st, warmup=16, want_e2e=True)
+        other[wl] = {k: r[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "timing", "roofline", "e2e",
+                                       "gpu_launches", "checksum_sum_u", "checksum_expected")}
+        other[wl]["config"] = {k: r["config"][k] for k in ("workload", "lattice", "nodes", "tiling")}
+        r1 = bench_lattice(wl, a, local=local, steps=20, warmup=5, fuse=False, want_e2e=False)
+        other[wl]["one_step_per_launch"] = {"value": r1["value"], "ms_per_step": r1["ms_per_step"],
+                                            "roofline_frac": r1["roofline"]["frac"]}
+    other["cfg5-ensemble"] = ensemble_short(local)
+    other["cfg1-batch"] = cfg1_short(local, cpu=not args.no_cpu)
+    out["other_configs"] = other
+    return out
+
+
+def ensemble_short(local):
+    """BASELINE configs[4] on this GPU: 65 536 independent 13x13x7 simulations in one launch (3 sweeps, the last 2 timed)."""
+    import tetrakis_sim_b200 as tk
+
+    specs, damp, dt = tk.sweep_grid(13, 7, np.linspace(0.5, 4.0, 64), np.linspace(0.0, 0.05, 32),
+                                    np.linspace(0.02, 0.2, 32))
+    kms, walls, res = [], [], None
+    for it in range(3):
+        t0 = time.perf_counter()
+        res, _ = tk.run_ensemble_sharded(specs, 50, c=1.0, dt=dt, damping=damp, dist=None, device=local, gather=False)
+        walls.append(time.perf_counter() - t0)
+        kms.append(res.elapsed_ms)
+    k, wl = float(np.mean(kms[1:])), float(np.mean(walls[1:]))
+    return {"value": res.node_updates / (k * 1e-3) / 1e9, "unit": UNIT, "ms_per_sweep": k,
+            "e2e": {"value": res.node_updates / wl / 1e9, "seconds": wl,
+                    "includes": "mask/parameter upload, kernel, series + spectra + dominant bins D2H"},
+            "config": {"workload": "cfg5-ensemble", "simulations": 65536, "lattice": "3-D tetrakis 13x13x7, 50 steps each",
+                       "note": "state resident in shared memory: the HBM roofline does not apply"},
+            "gpu_launches": 1}
+
+
+def ensemble_sharded_short(dist, local):
+    """BASELINE configs[4] over the ranks of this launch: the 65 536 simulations block-distributed, no data-path
+    communication; 3 sweeps, the last 2 timed; device time = the slowest rank's kernel (strong scaling: the sweep
+    is fixed)."""
+    import torch
+
+    import tetrakis_sim_b200 as tk
+
+    specs, damp, dt = tk.sweep_grid(13, 7, np.linspace(0.5, 4.0, 64), np.linspace(0.0, 0.05, 32),
+                                    np.linspace(0.02, 0.2, 32))
+    kms, walls, res = [], [], None
+    for it in range(3):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, _ = tk.run_ensemble_sharded(specs, 50, c=1.0, dt=dt, damping=damp, dist=dist, device=local, gather=False)
+        torch.cuda.synchronize()
+        walls.append(time.perf_counter() - t0)
+        kms.append(res.elapsed_ms)
+    t = torch.tensor([float(res.node_updates), float(np.mean(kms[1:])), float(np.mean(walls[1:]))],
+                     dtype=torch.float64, device=f"cuda:{local}")
+    upd = t[:1].clone()
+    dist.all_reduce(upd)
+    mx = t[1:].clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    updates, k, wl = float(upd.item()), float(mx[0].item()), float(mx[1].item())
+    return {"value": updates / (k * 1e-3) / 1e9, "unit": UNIT, "ms_per_sweep": k, "scaling": "strong",
+            "n_gpus": dist.get_world_size(),
+            "e2e": {"value": updates / wl / 1e9, "seconds": wl,
+                    "includes": "mask/parameter upload, kernel, series + spectra + dominant bins D2H (slowest rank)"},
+            "config": {"workload": "cfg5-ensemble", "simulations": 65536, "lattice": "3-D tetrakis 13x13x7, 50 steps each",
+                       "parallelism": f"simulations block-distributed over {dist.get_world_size()} GPUs, no communication"}}
+
+
+def cfg1_short(local, cpu=True):
+    """BASELINE configs[0] through the drop-in: run_wave_sim on the networkx graph (generic sliced-ELL kernel, results
+    bit-identical to the reference) and on the LatticeSpec (structured kernel), wall clock of the call; beside it the
+    literal CPU restatement on one core."""
+    import warnings
+
+    import tetrakis_sim_b200 as tk
+
+    spec = tk.LatticeSpec(size=11, dim=3, layers=7, defect="blackhole", radius=2.5)
+    kick = spec.kick_node()
+    G = spec.to_networkx()
+    out = {"config": {"workload": "cfg1-batch", "lattice": "3-D tetrakis 11x11x7, black hole r=2.5, 50 steps, dt 0.2",
+                      "nodes": spec.num_nodes}}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        for name, obj in (("run_wave_sim(G)", G), ("run_wave_sim(LatticeSpec)", spec)):
+            best = 1e9
+            for _ in range(5):
+                t0 = time.perf_counter()
+                h = tk.run_wave_sim(obj, steps=50, initial_data={kick: 1.0}, c=1.0, dt=0.2, device=local)
+                best = min(best, time.perf_counter() - t0)
+            out[name] = {"wall_s": best, "value": spec.num_nodes * 50 / best / 1e9, "unit": UNIT,
+                         "device_ms": h.elapsed_ms}
+    if cpu:
+        out["cpu_literal_1_core"] = cpu_literal_cfg1()
+    out["reference_python_networkx_s"] = 0.593  # SURVEY.md section 3a, measured on this image's host
+    return out
 
 
 def _csr_tetrakis(S, L):
@@ -554,6 +764,8 @@ def main():
     ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--layers", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="N=1 default: only the cfg2 line, without sharded_3d / other_configs")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                     help="f32 = optional fp32 state mode (12 B/update; NOT the parity mode)")
     args = ap.parse_args()
@@ -597,12 +809,17 @@ def main():
     # scaling) -- followed in the same launch by the layer-slab run of the 3-D lattice with the black hole
     from tetrakis_sim_b200.sheet import bench_sheet
 
+    import torch.distributed as dist
+
     line = bench_sheet(args, emit=False, keep_pg=True)
-    slab = bench_slabs(args, emit=False)
+    slab = bench_slabs(args, emit=False, keep_pg=True)
+    ens = ensemble_sharded_short(dist, int(os.environ.get("LOCAL_RANK", str(rank))))
+    dist.destroy_process_group()
     if rank == 0:
         line["sharded_3d"] = {k: slab[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "e2e",
-                                                   "gpu_launches", "single_gpu_same_workload",
-                                                   "checksum_sum_u", "checksum_expected")}
+                                                   "gpu_launches", "single_gpu_same_workload", "timing", "parity",
+                                                   "checksum_sum_u", "checksum_expected") if k in slab}
+        line["ensemble"] = ens
         print(json.dumps(line), flush=True)
     return 0
 

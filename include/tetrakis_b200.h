@@ -135,7 +135,12 @@ typedef struct tk_run_args {
     int64_t history_stride;     /* 0 or 1: history_out holds every state; k > 1: snapshots of states
                                    0, k, 2k, ... (floor(steps/k)+1 rows) for runs whose full history
                                    would not fit anywhere */
+    uint64_t flags;             /* TK_RUN_* bits */
 } tk_run_args;
+
+/* tk_run_args.flags: one step per launch (24 B per node update) even where K-step passes would apply --
+ * what a slab of a multi-GPU run does, so single-GPU denominators of weak-scaling series use it. */
+#define TK_RUN_NO_FUSE 0x1u
 
 /* physics.py:106-129: `steps` leapfrog updates, synchronous.  The state stays on the device, so
  * consecutive calls continue the same simulation. */

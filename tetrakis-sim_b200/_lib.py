@@ -58,7 +58,7 @@ class RunArgs(ctypes.Structure):
         ("steps", c_int64), ("coeff", c_double), ("damping", c_double),
         ("n_probes", c_int64), ("probe_index", c_void_p), ("probe_out", c_void_p),
         ("history_out", c_void_p), ("energy_out", c_void_p), ("elapsed_ms", c_void_p),
-        ("step_kernel_ms", c_void_p), ("history_stride", c_int64),
+        ("step_kernel_ms", c_void_p), ("history_stride", c_int64), ("flags", ctypes.c_uint64),
     ]  # fmt: skip
 
 
@@ -345,12 +345,13 @@ class Plan:
     # -- stepping -----------------------------------------------------------------------------
     def run(self, steps, coeff, damping, *, probes=None, history=False, timed=False,
             probe_out=None, history_out=None, energy=False, history_stride=1,
-            kernel_timing=False):  # fmt: skip
+            kernel_timing=False, fuse=True):  # fmt: skip
         """``steps`` leapfrog updates.  Returns dict(probes, history, energy, elapsed_ms, ...).
 
         ``timed``: CUDA-event time of the whole stepping loop.  ``kernel_timing``: additionally the summed
         event time of the step kernels alone (bench.py's roofline); it forces direct launches, whereas
-        launch-bound runs are otherwise replayed from a captured CUDA graph."""
+        launch-bound runs are otherwise replayed from a captured CUDA graph.  ``fuse=False``: one step per launch
+        even where K-step passes would apply (TK_RUN_NO_FUSE)."""
         steps = int(steps)
         pidx = _arr(probes if probes is not None else [], np.int64)
         pout = None
@@ -366,7 +367,7 @@ class Plan:
         a = RunArgs(steps, float(coeff), float(damping), len(pidx), _p(pidx), _p(pout), _p(hout),
                     _p(eout), ctypes.cast(ctypes.byref(ms), c_void_p) if timed else None,
                     ctypes.cast(ctypes.byref(kms), c_void_p) if kernel_timing else None,
-                    max(int(history_stride), 1))  # fmt: skip
+                    max(int(history_stride), 1), 0 if fuse else 1)  # fmt: skip
         check(lib().tk_plan_run(self._h, ctypes.byref(a)))
         return {"probes": pout, "history": hout, "energy": eout,
                 "elapsed_ms": ms.value if timed else None,

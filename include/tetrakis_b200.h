@@ -50,6 +50,10 @@ const char *tk_last_error(void);
 int tk_device_count(int *count);
 int tk_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major,
                    int *cc_minor, int64_t *total_mem_bytes);
+/* The library keeps freed device blocks of up to 256 MB (at most 2 GB per device) for reuse by later plans, because
+ * driver allocation calls cost more than a small simulation; this returns them to the driver.  TK_DEV_CACHE=0
+ * disables the cache. */
+int tk_device_trim(int device);
 
 /* ------------------------------------------------------------------------------------------
  * Graph plan: any networkx graph.  Replaces the per-call precompute of physics.py:56-64,93-102

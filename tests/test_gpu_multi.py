@@ -17,7 +17,9 @@ SPEC = dict(size=48, dim=3, layers=13, defect="blackhole", radius=4.2)
 STEPS, COEFF, DAMPING = 25, 0.003, 0.005
 
 
-def _worker(rank, world, port, out, transport):
+def _worker(rank, world, port, out, transport, jitter=False, steps=STEPS):
+    import time
+
     import torch
     import torch.distributed as dist
 
@@ -42,7 +44,15 @@ def _worker(rank, world, port, out, transport):
         mine = {runner.local_index(g): v for g, v in kicks.items() if runner.owns(g)}
         backend.set_state_sparse(list(mine), list(mine.values()))
         runner.begin(COEFF, DAMPING)
-        for _ in range(STEPS):
+        rng = np.random.default_rng(1234 + 17 * rank)  # every rank draws its own delays
+        for _ in range(steps):
+            if jitter:
+                # a rank that runs ahead or falls behind by random amounts: up to ~2 ms of device stall on its
+                # main stream and up to 1 ms of host stall, so flags and halos are produced and consumed out of step
+                if rng.random() < 0.5:
+                    torch.cuda._sleep(int(rng.integers(1, 4_000_000)))
+                if rng.random() < 0.3:
+                    time.sleep(float(rng.random()) * 1e-3)
             runner.step()
         runner.finish()
         torch.cuda.synchronize()
@@ -81,3 +91,33 @@ def test_multi_gpu_slab_run_matches_the_oracle(world, transport, tmp_path):
     ref = wo.run_structured(spec.size, spec.layers, flags, None, None, [], u0, STEPS, COEFF, DAMPING)["u"]
     assert rel_inf(got, ref) < 1e-12
     assert int(np.load(tmp_path / "maxdeg.npy")[0]) == 3 + 2 * (spec.size - 1) + 2
+
+
+@pytest.mark.parametrize("transport", ["p2p", "p2p-split", "p2p-copy", "nccl"])
+def test_halo_flag_protocol_survives_random_delays(transport, tmp_path):
+    """Stress of the stream-ordered flag protocol (cuStreamWriteValue64 / cuStreamWaitValue64 on peer memory): every
+    rank stalls its stream and its host thread by random, rank-specific amounts between steps, so neighbours run up to
+    a step ahead of or behind each other for 60 steps; the result must still be the oracle's (a halo plane that was
+    overwritten too early, or read too early, would show up here)."""
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    steps = 60
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(world, port, str(tmp_path), transport, True, steps), nprocs=world, join=True)
+    spec = tk.LatticeSpec(**SPEC)
+    got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)])
+    flags = np.full(spec.num_slots, 3, dtype=np.uint8)
+    si, sf, _, _ = spec.specials()
+    flags[si] = sf
+    u0 = np.zeros(spec.num_slots)
+    u0[spec.index(spec.kick_node())] = 1.0
+    u0[spec.index((0, 0, 0, "B"))] = -0.5
+    u0[spec.index((spec.size - 1, 1, spec.layers - 1, "D"))] = 0.25
+    ref = wo.run_structured(spec.size, spec.layers, flags, None, None, [], u0, steps, COEFF, DAMPING)["u"]
+    assert rel_inf(got, ref) < 1e-12

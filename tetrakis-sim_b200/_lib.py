@@ -19,7 +19,7 @@ TK_OK, TK_ERR_INVALID, TK_ERR_CUDA, TK_ERR_NOMEM, TK_ERR_NO_DEVICE = 0, 1, 2, 3,
 
 # every symbol declared in include/tetrakis_b200.h (tests check the .so exports all of them)
 ABI_SYMBOLS = (
-    "tk_abi_version", "tk_last_error", "tk_device_count", "tk_device_info",
+    "tk_abi_version", "tk_last_error", "tk_device_count", "tk_device_info", "tk_device_trim",
     "tk_graph_plan_create", "tk_lattice_plan_create", "tk_lattice_plan_create_ex",
     "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
@@ -95,6 +95,7 @@ def lib():
     L.tk_device_count.argtypes = [POINTER(c_int)]
     L.tk_device_info.argtypes = [c_int, c_char_p, c_int, POINTER(c_int), POINTER(c_int),
                                  POINTER(c_int), POINTER(c_int64)]  # fmt: skip
+    L.tk_device_trim.argtypes = [c_int]
     L.tk_graph_plan_create.argtypes = [c_int, c_int64, P, P, P, P, P, POINTER(P)]
     L.tk_lattice_plan_create.argtypes = [c_int, POINTER(LatticeDesc), POINTER(P)]
     L.tk_lattice_plan_create_ex.argtypes = [c_int, POINTER(LatticeDesc), ctypes.c_uint32, POINTER(P)]
@@ -172,6 +173,11 @@ def device_info(device: int = 0) -> dict:
                                ctypes.byref(mnr), ctypes.byref(mem)))  # fmt: skip
     return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value),
             "total_mem": mem.value}  # fmt: skip
+
+
+def device_trim(device: int = 0) -> None:
+    """Return the library's cache of freed device blocks to the driver (tk_device_trim)."""
+    check(lib().tk_device_trim(device))
 
 
 def _p(a):

@@ -34,22 +34,37 @@ class CompiledGraph:
 
 
 def graph_arrays(G):
-    """(nodes, index, rowptr, colidx, degree, inv_mass, potential) -- physics.py:56-64, 93-102."""
+    """(nodes, index, rowptr, colidx, degree, inv_mass, potential) -- physics.py:56-64, 93-102.
+
+    One pass over the adjacency dicts with C-level iterators (``map`` / ``chain``): no Python-level loop per edge."""
+    from itertools import chain
+
     nodes = list(G.nodes)
-    index = {n: i for i, n in enumerate(nodes)}
     n = len(nodes)
-    adj = G.adj
-    counts = np.fromiter((len(adj[v]) for v in nodes), dtype=np.int64, count=n)
+    index = dict(zip(nodes, range(n)))
+    adj = G._adj if hasattr(G, "_adj") else {v: G.adj[v] for v in nodes}
+    if n and next(iter(adj)) is not nodes[0] or len(adj) != n:  # adjacency dict in another order than the node dict
+        rows = [adj[v] for v in nodes]
+    else:
+        rows = adj.values()
+    counts = np.fromiter(map(len, rows), dtype=np.int64, count=n)
     rowptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(counts, out=rowptr[1:])
-    colidx = np.fromiter(
-        (index[m] for v in nodes for m in adj[v]), dtype=np.int32, count=int(rowptr[-1])
-    )
-    deg_map = dict(G.degree(nodes))
-    degree = np.fromiter((deg_map[v] for v in nodes), dtype=np.float64, count=n)
+    colidx = np.fromiter(map(index.__getitem__, chain.from_iterable(rows)), dtype=np.int32, count=int(rowptr[-1]))
+    # G.degree: the adjacency length, a self-loop counting twice (networkx reportviews.DegreeView)
+    degree = counts.astype(np.float64)
+    if G.is_multigraph():
+        deg_map = dict(G.degree(nodes))
+        degree = np.fromiter((deg_map[v] for v in nodes), dtype=np.float64, count=n)
+    else:
+        # a self-loop (i, i) shows up as colidx == row
+        loops = np.flatnonzero(colidx == np.repeat(np.arange(n, dtype=np.int32), counts))
+        if loops.size:
+            np.add.at(degree, colidx[loops], 1.0)
     inv_mass = np.ones(n, dtype=np.float64)
     potential = np.zeros(n, dtype=np.float64)
-    for v, attrs in G.nodes(data=True):
+    node_attrs = G._node if hasattr(G, "_node") else dict(G.nodes(data=True))
+    for v, attrs in node_attrs.items():
         if attrs:
             if "mass" in attrs:
                 m = float(attrs["mass"])

@@ -7,6 +7,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <unordered_map>
@@ -21,6 +23,118 @@
 namespace {
 
 thread_local std::string g_err;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-memory cache.  A run_wave_sim call on a reference-sized graph makes ~20 cudaMalloc / cudaFree calls (plan
+// arrays, probe and history staging, kick upload); on the B200 boxes of this pool a single one of them takes anything
+// from 50 us to hundreds of ms (measured: scripts/micro/alloc_cost.cu), which is more than the whole simulation.  Freed
+// blocks up to 256 MB are therefore kept per device (at most 2 GB in total) and handed out again to requests of about
+// the same size; everything else goes straight to the driver.  tk_device_trim() returns the cache to the driver;
+// TK_DEV_CACHE=0 switches it off.  A block is only reused after cudaDeviceSynchronize() at the time it was freed.
+struct DevCache {
+    std::mutex mu;
+    std::unordered_map<void *, std::pair<int, size_t>> live;     // ptr -> (device, capacity)
+    std::multimap<size_t, void *> free_[16];                     // per device: capacity -> ptr
+    size_t cached[16] = {0};
+    int enabled = -1;
+};
+DevCache &dev_cache()
+{
+    static DevCache *c = new DevCache();  // never destroyed: the CUDA context may be gone at exit
+    return *c;
+}
+constexpr size_t kCacheMaxBlock = (size_t)256 << 20, kCacheMaxTotal = (size_t)2 << 30;
+
+size_t cache_class(size_t bytes)
+{
+    if (bytes <= 65536) return (bytes + 511) / 512 * 512;
+    size_t g = 4096;  // granule: 1/8 of the next power of two below the size
+    while (g * 16 <= bytes) g <<= 1;
+    return (bytes + g - 1) / g * g;
+}
+
+cudaError_t tk_malloc(void **p, size_t bytes)
+{
+    DevCache &c = dev_cache();
+    if (c.enabled < 0) {
+        const char *e = getenv("TK_DEV_CACHE");
+        c.enabled = (e && *e == '0') ? 0 : 1;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!c.enabled || dev < 0 || dev >= 16) return cudaMalloc(p, bytes);
+    const size_t want = cache_class(std::max<size_t>(bytes, 1));
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.free_[dev].lower_bound(want);
+        if (it != c.free_[dev].end() && it->first <= want + want / 4 + 65536) {
+            *p = it->second;
+            c.cached[dev] -= it->first;
+            c.live[*p] = {dev, it->first};
+            c.free_[dev].erase(it);
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e == cudaErrorMemoryAllocation) {  // give the cache back to the driver and try once more
+        cudaGetLastError();
+        std::vector<void *> drop;
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            for (auto &kv : c.free_[dev]) drop.push_back(kv.second);
+            c.free_[dev].clear();
+            c.cached[dev] = 0;
+        }
+        for (void *q : drop) cudaFree(q);
+        e = cudaMalloc(p, want);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(c.mu);
+        c.live[*p] = {dev, want};
+    }
+    return e;
+}
+
+cudaError_t tk_free(void *p)
+{
+    if (!p) return cudaSuccess;
+    DevCache &c = dev_cache();
+    int dev = -1;
+    size_t cap = 0;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.live.find(p);
+        if (it != c.live.end()) {
+            dev = it->second.first;
+            cap = it->second.second;
+            c.live.erase(it);
+        }
+    }
+    if (dev < 0) return cudaFree(p);
+    if (cap > kCacheMaxBlock) return cudaFree(p);
+    cudaDeviceSynchronize();  // nobody still works on the block (cudaFree would have synchronised too)
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.cached[dev] + cap > kCacheMaxTotal) {
+        cudaFree(p);
+    } else {
+        c.free_[dev].emplace(cap, p);
+        c.cached[dev] += cap;
+    }
+    return cudaSuccess;
+}
+
+int cached_sm_count(int device)
+{
+    static int sm[16] = {0};
+    if (device >= 0 && device < 16 && sm[device] > 0) return sm[device];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        cudaGetLastError();
+        n = 148;
+    }
+    if (device >= 0 && device < 16) sm[device] = n;
+    return n;
+}
 
 int fail(int code, const char *fmt, ...)
 {
@@ -66,7 +180,7 @@ int dev_alloc(T **p, size_t count)
 {
     *p = nullptr;
     if (count == 0) count = 1;
-    TK_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+    TK_CUDA(tk_malloc((void **)p, count * sizeof(T)));
     return TK_OK;
 }
 
@@ -180,9 +294,7 @@ int plan_common_init(tk_plan *p, int device)
     p->device = device;
     TK_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     p->own_stream = true;
-    cudaDeviceProp prop;
-    TK_CUDA(cudaGetDeviceProperties(&prop, device));
-    p->sm_count = prop.multiProcessorCount;
+    p->sm_count = cached_sm_count(device);  // (cudaGetDeviceProperties costs 2-15 ms per call here)
     return TK_OK;
 }
 

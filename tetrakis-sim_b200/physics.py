@@ -22,6 +22,9 @@ Extra keyword-only arguments (all optional; the positional signature is the refe
   snapshot_every  (LatticeSpec, record="all") keep only states 0, k, 2k, ... in ``history.array`` --
            whole-lattice snapshots for runs whose full history would not fit (the probe series is
            still recorded at every step)
+  final_state  (LatticeSpec, record="probes") False: do not copy the whole final state to the host
+           (``history.final_state`` stays None) -- 2.1 GB and ~40 ms over PCIe at BASELINE config 2, when all the caller
+           wants is the probes' time series
   energy   also return ``history.energy``: the staggered discrete energy between consecutive states,
            ``steps`` values, conserved to rounding when damping == 0 (a new diagnostic; the reference
            computes no energy -- SURVEY.md section 2)
@@ -38,7 +41,11 @@ from . import _lib
 from .compiler import CompiledGraph, compile_graph, compile_lattice, structured_from_graph
 from .lattice import LatticeSpec
 
-_EAGER_DICT_LIMIT = 2_000_000  # (steps+1)*N entries above this -> lazy row views instead of dicts
+# (steps+1)*N entries above this -> read-only row views over the history array instead of eager dicts (building
+# 51 dicts of 3 064 entries costs 20 ms -- forty times the simulation; every consumer in the reference only reads:
+# state.get(node), iteration, .values(): physics.py:162, plot.py:153,274, tests/test_invariants.py:88-89).
+# TETRAKIS_B200_EAGER_STATES=1 forces plain dicts.
+_EAGER_DICT_LIMIT = 60_000
 
 
 class SimulationHistory(list):
@@ -162,7 +169,9 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
             arr = out["history"]
             if comp.state_index is not None:
                 arr = np.ascontiguousarray(arr[:, comp.state_index])
-            if (steps + 1) * n <= _EAGER_DICT_LIMIT:
+            import os
+
+            if (steps + 1) * n <= _EAGER_DICT_LIMIT or os.environ.get("TETRAKIS_B200_EAGER_STATES") == "1":
                 states = [dict(zip(nodes, row)) for row in arr.tolist()]
                 if extra0:
                     states[0].update(extra0)
@@ -190,7 +199,7 @@ def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, pro
 
 
 def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device, record, probes, energy,
-                 dtype="float64", snapshot_every=1, steps_requested=None):
+                 dtype="float64", snapshot_every=1, steps_requested=None, final_state=True):
     plan = compile_lattice(spec, device=device, dtype=dtype)
     try:
         effective_dt, metadata = _cfl(plan.max_degree, c, dt, steps if steps_requested is None else steps_requested,
@@ -216,7 +225,7 @@ def _run_lattice(spec: LatticeSpec, steps, initial_data, c, dt, damping, device,
         hist.snapshot_every = snapshot_every
         if hist.array is not None and steps % max(snapshot_every, 1) == 0:
             hist.final_state = hist.array[-1]
-        else:
+        elif final_state:
             hist.final_state = plan.get_state()
         hist.elapsed_ms = out["elapsed_ms"]
         hist.energy = None if out["energy"] is None else out["energy"] * (c * c)
@@ -244,6 +253,7 @@ def run_wave_sim(
     dtype: str = "float64",
     snapshot_every: int = 1,
     reorder: str = "auto",
+    final_state: bool = True,
 ) -> SimulationHistory:
     """Simulate the discrete wave equation on ``G`` (reference physics.py:41-131).
 
@@ -256,7 +266,7 @@ def run_wave_sim(
         raise ValueError("path must be 'auto', 'graph' or 'structured'")
     if isinstance(G, LatticeSpec):
         return _run_lattice(G, steps, initial_data, c, dt, damping, device, record or "probes", probes, energy,
-                            dtype, max(int(snapshot_every), 1), steps_requested)
+                            dtype, max(int(snapshot_every), 1), steps_requested, final_state)
     if dtype != "float64":
         raise ValueError("dtype='float32' is available for LatticeSpec input only")
     return _run_graph(G, steps, initial_data, c, dt, damping, device, path, record or "all", probes, energy,

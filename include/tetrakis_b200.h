@@ -310,6 +310,18 @@ typedef struct tk_ensemble_desc {
 int tk_ensemble_run(int device, const tk_ensemble_desc *desc, double *probe_series,
                     double *spectrum, int64_t *argmax, double *elapsed_ms);
 
+/* Same, plus the spectral and time-series features of every simulation's probe series computed in the kernel's epilogue
+ * (reference tetrakis_sim/evals/features.py:11-81, what tetrakis-eval generate writes per record, evals/dataset.py:146-153):
+ * features[n_sims][TK_ENSEMBLE_NFEAT] =
+ *   0 dominant bin, 1 spectral centroid, 2 spectral bandwidth (both in bins: divide by (steps+1)*dt_eff for the
+ *   reference's frequency units), 3 peak amplitude, 4 low/high ratio, 5-9 bins of the five largest peaks (-1 = none),
+ *   10-14 their magnitude relative to the maximum, 15 rms and 16 max |.| of the series, 17 sum of the half spectrum;
+ * all on the non-negative-frequency half of the spectrum (features.py:18-21).  probe_series / spectrum / argmax may be
+ * NULL when only the features are wanted (18 doubles per simulation instead of 2 x (steps+1)). */
+#define TK_ENSEMBLE_NFEAT 18
+int tk_ensemble_run_ex(int device, const tk_ensemble_desc *desc, double *probe_series, double *spectrum,
+                       int64_t *argmax, double *features, double *elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

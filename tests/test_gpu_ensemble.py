@@ -86,3 +86,29 @@ def test_config5_grid_spot_check_against_the_reference():
         assert rel_inf(res.series[g], z["series"][i]) < 1e-12
         assert rel_inf(res.spectrum[g], z["spectra"][i]) < 1e-11
         assert wo.folded_bin(res.spectrum[g]) == wo.folded_bin(z["spectra"][i])
+
+
+@pytest.mark.parametrize("steps", [40, 51, 7])
+def test_device_features_match_the_host_restatement(steps):
+    """The ensemble kernel's epilogue computes the spectral / time-series features of tetrakis-eval generate
+    (reference evals/features.py:11-81) on the device; tetrakis_sim_b200.features is the NumPy restatement of the same
+    definitions.  Odd and even series lengths (the non-negative half has (n+1)//2 bins), damped and undamped members."""
+    from tetrakis_sim_b200.features import spectral_features, timeseries_features
+
+    radii, dampings, dts = [0.5, 1.7, 2.5], [0.0, 0.03], [0.05, 0.2]
+    specs, damp, dt = tk.sweep_grid(11, 5, radii, dampings, dts)
+    res = tk.run_ensemble(specs, steps, c=1.0, dt=dt, damping=damp, features=True)
+    only = tk.run_ensemble(specs, steps, c=1.0, dt=dt, damping=damp, features=True, series=False, spectrum=False)
+    assert only.series is None and only.spectrum is None and np.array_equal(only.features, res.features)
+    for i in range(len(specs)):
+        freq = np.fft.fftfreq(steps + 1, d=float(res.effective_dt[i]))
+        want = spectral_features(freq, res.spectrum[i])
+        want.update(timeseries_features(res.series[i]))
+        got = res.feature_dict(i)
+        assert set(got) == set(want)
+        for k, v in want.items():
+            if k.startswith("peak_i_"):
+                assert got[k] == v, (i, k)
+            else:
+                assert got[k] == pytest.approx(v, rel=1e-11, abs=1e-13), (i, k)
+        assert abs(got["dominant_freq"]) == pytest.approx(abs(res.dominant_freq[i]), rel=1e-12)

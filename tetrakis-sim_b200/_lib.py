@@ -28,7 +28,7 @@ ABI_SYMBOLS = (
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
     "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
     "tk_lattice_ipc_export", "tk_ipc_open", "tk_ipc_close", "tk_lattice_peer_attach",
-    "tk_lattice_set_push_mode", "tk_lattice_push_halos", "tk_lattice_signal", "tk_lattice_wait", "tk_lattice_state_ptrs", "tk_dft_abs", "tk_ensemble_run",
+    "tk_lattice_set_push_mode", "tk_lattice_push_halos", "tk_lattice_signal", "tk_lattice_wait", "tk_lattice_state_ptrs", "tk_dft_abs", "tk_ensemble_run", "tk_ensemble_run_ex",
 )  # fmt: skip
 
 
@@ -137,6 +137,7 @@ def lib():
                                     POINTER(c_int32)]  # fmt: skip
     L.tk_dft_abs.argtypes = [c_int, P, c_int64, c_int64, P, P]
     L.tk_ensemble_run.argtypes = [c_int, POINTER(EnsembleDesc), P, P, P, POINTER(c_double)]
+    L.tk_ensemble_run_ex.argtypes = [c_int, POINTER(EnsembleDesc), P, P, P, P, POINTER(c_double)]
     for name in ABI_SYMBOLS:
         fn = getattr(L, name)
         if name not in ("tk_last_error",):

@@ -26,7 +26,94 @@ struct EnsDev {
     double *series;    // [n_sims][steps+1]
     double *spectrum;  // [n_sims][steps+1] or nullptr
     long long *argmax; // [n_sims] or nullptr
+    double *features;  // [n_sims][kEnsNFeat] or nullptr (needs spectrum): see ens_features
 };
+
+// Spectral + time-series features of one simulation's probe series, in the epilogue of the ensemble kernel
+// (reference tetrakis_sim/evals/features.py:11-81, evaluated on the non-negative-frequency half of the spectrum):
+//   0 dominant bin   1 centroid [bins]   2 bandwidth [bins]   3 peak amplitude   4 low/high ratio
+//   5-9 bins of the five largest peaks (-1 = none)   10-14 their magnitude / (max + 1e-12)
+//   15 rms of the series   16 max |series|   17 sum of the half spectrum
+// Frequencies are in BINS: f = bin / ((steps+1) dt_eff), which the host applies (the kernel never sees dt).
+constexpr int kEnsNFeat = 18;
+
+__device__ __forceinline__ void ens_features(const double *__restrict__ a, const double *__restrict__ v, int nt,
+                                             double *__restrict__ out, int lane)
+{
+    const int nh = (nt + 1) / 2;  // bins with fftfreq >= 0: 0 .. ceil(nt/2) - 1   (features.py:18-21)
+    const int half = nh / 2;
+    double total = 0.0, ka = 0.0, low = 0.0, high = 0.0, amax = -1.0, sq = 0.0, vpk = 0.0;
+    int imax = 0;
+    for (int k = lane; k < nh; k += 32) {
+        const double x = a[k];
+        total += x;
+        ka += (double)k * x;
+        if (k < half) low += x; else high += x;
+        if (x > amax) { amax = x; imax = k; }
+    }
+    for (int j = lane; j < nt; j += 32) {
+        sq += v[j] * v[j];
+        vpk = fmax(vpk, fabs(v[j]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+        ka += __shfl_xor_sync(0xffffffffu, ka, o);
+        low += __shfl_xor_sync(0xffffffffu, low, o);
+        high += __shfl_xor_sync(0xffffffffu, high, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        vpk = fmax(vpk, __shfl_xor_sync(0xffffffffu, vpk, o));
+        const double oa = __shfl_xor_sync(0xffffffffu, amax, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, imax, o);
+        if (oa > amax || (oa == amax && oi < imax)) { amax = oa; imax = oi; }  // np.argmax: the first maximum
+    }
+    double feat[kEnsNFeat];
+#pragma unroll
+    for (int i = 0; i < kEnsNFeat; ++i) feat[i] = 0.0;
+#pragma unroll
+    for (int i = 5; i < 10; ++i) feat[i] = -1.0;
+    feat[15] = sqrt(sq / (double)nt);
+    feat[16] = vpk;
+    feat[17] = total;
+    if (nh > 0 && total > 0.0) {
+        const double kc = ka / total;
+        double bw = 0.0;
+        for (int k = lane; k < nh; k += 32) bw += ((double)k - kc) * ((double)k - kc) * a[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bw += __shfl_xor_sync(0xffffffffu, bw, o);
+        feat[0] = (double)imax;
+        feat[1] = kc;
+        feat[2] = sqrt(bw / total);
+        feat[3] = amax;
+        feat[4] = low / (high + 1e-12);
+        // five largest peaks, descending (ties: lower bin first)
+        int taken[5] = {-1, -1, -1, -1, -1};
+        const int kmax = nh < 5 ? nh : 5;
+        for (int j = 0; j < kmax; ++j) {
+            double best = -1.0;
+            int bi = 0x7fffffff;
+            for (int k = lane; k < nh; k += 32) {
+                bool used = false;
+#pragma unroll
+                for (int t = 0; t < 5; ++t) used |= taken[t] == k;
+                if (!used && (a[k] > best || (a[k] == best && k < bi))) { best = a[k]; bi = k; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            taken[j] = bi;
+            feat[5 + j] = (double)bi;
+            feat[10 + j] = best / (amax + 1e-12);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kEnsNFeat; ++i) out[i] = feat[i];
+    }
+}
 
 constexpr int kEnsMaxCorr = 32;
 
@@ -264,6 +351,10 @@ ensemble_kernel(const __grid_constant__ EnsDev P, long long n_sims)
                 const double mag = hypot(re, imag);
                 P.spectrum[(size_t)sim * nt + k] = mag;
                 if (fits) spec[k] = mag;
+            }
+            if (P.features) {  // one warp: spectral + time-series features of this simulation (fits: see host check)
+                __syncthreads();
+                if (tid < 32) ens_features(spec, series, nt, P.features + (size_t)sim * kEnsNFeat, tid);
             }
             if (P.argmax) {
                 __syncthreads();

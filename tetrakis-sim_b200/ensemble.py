@@ -33,6 +33,23 @@ class EnsembleResult:
     kick_nodes: list  # reference node tuples
     elapsed_ms: float  # device time of the ensemble kernel
     node_updates: int  # surviving nodes x steps summed over simulations
+    features: np.ndarray | None = None  # (n_sims, 18) device-computed features (tk_ensemble_run_ex), or None
+
+    FEATURE_NAMES = ("dominant_freq", "spectral_centroid", "spectral_bandwidth", "peak_amplitude", "low_high_ratio",
+                     "peak_i_0", "peak_i_1", "peak_i_2", "peak_i_3", "peak_i_4",
+                     "peak_mag_0", "peak_mag_1", "peak_mag_2", "peak_mag_3", "peak_mag_4", "ts_rms", "ts_peak")
+
+    def feature_dict(self, i: int) -> dict:
+        """Record ``i`` with the reference's feature names and units (evals/features.py:11-81): the kernel reports
+        frequencies in bins, f = bin / ((steps+1) * dt_eff)."""
+        f = self.features[i]
+        nt = self.series.shape[1] if self.series is not None else self.nt
+        per_bin = 1.0 / (nt * float(self.effective_dt[i]))
+        out = {k: float(f[j]) for j, k in enumerate(self.FEATURE_NAMES)}
+        if f[17] > 0.0:
+            for k in ("dominant_freq", "spectral_centroid", "spectral_bandwidth"):
+                out[k] *= per_bin
+        return out
 
 
 def _spec_key(s: LatticeSpec):
@@ -71,10 +88,13 @@ def mask_arrays(spec: LatticeSpec, want_degrees: bool = False):
 
 
 def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, device: int = 0,
-                 spectrum: bool = True) -> EnsembleResult:  # fmt: skip
+                 spectrum: bool = True, features: bool = False, series: bool = True) -> EnsembleResult:  # fmt: skip
     """Run ``len(specs)`` independent simulations.  ``c``, ``dt``, ``damping`` are scalars or
     per-simulation arrays; ``kicks`` optional list of node tuples (default: the batch.py kick rule).
-    All specs must share (size, dim, layers); identical defects share one device mask."""
+    All specs must share (size, dim, layers); identical defects share one device mask.
+    ``features=True``: the spectral / time-series features of evals/features.py computed on the device
+    (``result.features``, ``result.feature_dict(i)``); with ``series=False, spectrum=False`` only those 18 numbers per
+    simulation come back to the host."""
     specs = list(specs)
     n = len(specs)
     if n == 0:
@@ -127,22 +147,26 @@ def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, devi
     corr_s = np.array([s for m in mask_data for _, _, s in m[2]], dtype=np.float64)
 
     nt = int(steps) + 1
-    series = np.empty((n, nt), dtype=np.float64)
+    want_series = series
+    series = np.empty((n, nt), dtype=np.float64) if want_series else None
     spec_out = np.empty((n, nt), dtype=np.float64) if spectrum else None
     arg = np.empty(n, dtype=np.int64) if spectrum else None
+    feat = np.empty((n, 18), dtype=np.float64) if features else None
     ms = ctypes.c_double(0.0)
     p = _lib._p
     d = _lib.EnsembleDesc(S, L, n_masks, p(bits), p(exc_off), p(exc_node), p(exc_im), p(exc_pot),
                           p(corr_off), p(corr_a), p(corr_b), p(corr_s), n, p(sim_mask), p(sim_kick),
                           None, p(coeff), p(damping), int(steps))  # fmt: skip
-    _lib.check(_lib.lib().tk_ensemble_run(device, ctypes.byref(d), p(series), p(spec_out), p(arg),
-                                          ctypes.byref(ms)))  # fmt: skip
+    _lib.check(_lib.lib().tk_ensemble_run_ex(device, ctypes.byref(d), p(series), p(spec_out), p(arg), p(feat),
+                                             ctypes.byref(ms)))  # fmt: skip
     if spectrum:
         freq = np.fft.fftfreq(nt)[arg] / eff  # fftfreq(nt, d=dt)[k] == fftfreq(nt)[k] / dt
     else:
         freq = None
     updates = int(sum(mask_data[m][4] for m in sim_mask)) * int(steps)
-    return EnsembleResult(series, spec_out, arg, freq, eff, clamp, maxdeg, kick_nodes, ms.value, updates)
+    res = EnsembleResult(series, spec_out, arg, freq, eff, clamp, maxdeg, kick_nodes, ms.value, updates, feat)
+    res.nt = nt
+    return res
 
 
 def run_ensemble_sharded(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, *, dist=None,

@@ -16,10 +16,7 @@ import json
 import random
 from pathlib import Path
 
-import numpy as np
-
 from .ensemble import mask_arrays, run_ensemble
-from .features import spectral_features, timeseries_features
 from .lattice import LatticeSpec
 
 SCHEMA_VERSION = 1
@@ -60,7 +57,10 @@ def generate_defect_classification_jsonl(out_path, *, n_per_class: int = 10, see
     out_path.parent.mkdir(parents=True, exist_ok=True)
     drawn = draw_specs(n_per_class, seed, size, dim, layers)
     specs = [s for _, s, _ in drawn]
-    res = run_ensemble(specs, steps, c=c, dt=dt, damping=damping, device=device)
+    # one launch: simulations, probe spectra and the spectral / time-series features all on the device; only the
+    # 18 feature values per simulation come back
+    res = run_ensemble(specs, steps, c=c, dt=dt, damping=damping, device=device, features=True, series=False,
+                       spectrum=False)
     cache: dict = {}
     with out_path.open("w", encoding="utf-8") as f:
         for i, (label, spec, extra) in enumerate(drawn):
@@ -75,7 +75,6 @@ def generate_defect_classification_jsonl(out_path, *, n_per_class: int = 10, see
             params = {"size": size, "dim": dim, "layers": layers, "steps": steps, "c": c, "dt_requested": dt, "damping": damping}
             params.update(extra)
             params["dt_used"] = float(res.effective_dt[i])
-            freq = np.fft.fftfreq(steps + 1, d=float(res.effective_dt[i]))
             feats = {
                 "n_nodes": float(n_alive),
                 "n_edges": float(n_edges),
@@ -84,8 +83,7 @@ def generate_defect_classification_jsonl(out_path, *, n_per_class: int = 10, see
                 "removed_node_count": float(spec.removed_count),
                 "singular_node_count": float(singular),
             }
-            feats.update(spectral_features(freq, res.spectrum[i]))
-            feats.update(timeseries_features(res.series[i]))
+            feats.update(res.feature_dict(i))  # ensemble_kernel epilogue (kernels_ensemble.cuh:ens_features)
             feats["kick_degree"] = float(deg[spec.index(kick)])
             feats["kick_dist2_center"] = float((kick[0] - ctr[0]) ** 2 + (kick[1] - ctr[1]) ** 2)
             rec = {"schema_version": SCHEMA_VERSION, "id": f"dc_{i + 1:05d}",

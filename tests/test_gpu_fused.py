@@ -117,7 +117,8 @@ def test_fused_passes_continue_from_a_dense_state_with_a_previous_level():
 
 
 def test_fusion_is_not_used_where_the_recurrences_do_not_close(monkeypatch):
-    """Defects, 3-D, full history, energy series: step by step."""
+    """Small lattices with defects / in 3-D (the cross scheme of kernels_cross.cuh starts at 2^21 nodes:
+    tests/test_gpu_cross.py), full history, energy series: step by step."""
     monkeypatch.setenv("TK_LAT_FUSE", "8")
     hole = tk.LatticeSpec(size=40, dim=2, defect="blackhole", radius=3.0)
     assert _run(hole, 32, None, 0.0, None).fused["steps_per_pass"] == 0
@@ -133,7 +134,7 @@ def test_fusion_is_not_used_where_the_recurrences_do_not_close(monkeypatch):
     assert full.fused["steps_per_pass"] == 0 and en.fused["steps_per_pass"] == 0
     assert _run(sheet, 32, None, 0.0, None).fused["steps_per_pass"] == 8
     assert _run(sheet, 1, None, 0.0, None).fused["steps_per_pass"] == 0
-    many = [sheet.node(i) for i in range(9)]  # more probes than a pass can record
+    many = [sheet.node(i) for i in range(65)]  # more probes than a pass records (64)
     assert _run(sheet, 32, None, 0.0, many).fused["steps_per_pass"] == 0
 
 
@@ -188,6 +189,22 @@ def test_fused_passes_record_eight_probes_sharing_cells_rows_and_warps():
     u0 = np.zeros(spec.num_slots)
     u0[ki], u0[cell + 6] = 1.0, 0.5
     ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, 0.01, pidx)
+    assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
+    assert rel_inf(hist.final_state, ref["u"]) < 1e-12
+
+
+def test_fused_passes_record_a_whole_row_of_probes():
+    """64 probes (a pass records up to 64; every CTA filters the list down to its own tile): one per 25 nodes along
+    a diagonal band of the sheet, so they fall into many different CTAs, rows and warps."""
+    S, steps = 200, 45
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.kick_node()
+    pidx = [((3 * i) % S * S + (7 * i + 5) % S) * 4 + i % 4 for i in range(64)]
+    hist = _run(spec, steps, {kick: 1.0}, 0.0, [spec.node(i) for i in pidx])
+    assert hist.fused["fused_steps"] == steps
+    u0 = np.zeros(spec.num_slots)
+    u0[spec.index(kick)] = 1.0
+    ref = _oracle(S, u0, None, steps, (1.0 * hist.dt) ** 2, 0.0, pidx)
     assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
     assert rel_inf(hist.final_state, ref["u"]) < 1e-12
 

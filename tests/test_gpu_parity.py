@@ -194,6 +194,41 @@ def test_device_dft_matches_numpy_fft(n):
     assert rel_inf(sb, np.abs(np.fft.fft(xb, axis=1))) < 1e-12 and ab.shape == (5,)
 
 
+@pytest.mark.parametrize("n", [2, 3, 51, 64, 1000, 4097, 10001, 65536, 100003])
+def test_chirp_z_spectrum_matches_the_direct_sum_and_numpy(n, monkeypatch):
+    """The O(N log N) path (Bluestein chirp-z over a power-of-two Stockham FFT, kernels_fft.cuh) against the direct
+    O(N^2) kernel -- its checker -- and numpy's FFT, batched, for lengths around powers of two and BASELINE config 2's
+    10 001 samples."""
+    rng = np.random.default_rng(n)
+    xb = rng.normal(size=(3, n)) + np.sin(np.arange(n) * 0.37)[None, :]
+    monkeypatch.setenv("TK_DFT", "chirp")
+    sc, ac = tk.dft_abs(xb)
+    ref = np.abs(np.fft.fft(xb, axis=1))
+    assert rel_inf(sc, ref) < 1e-12
+    if n <= 10001:
+        monkeypatch.setenv("TK_DFT", "direct")
+        sd, ad = tk.dft_abs(xb)
+        assert rel_inf(sc, sd) < 1e-12
+        assert [wo.folded_bin(a) for a in sc] == [wo.folded_bin(a) for a in sd]
+    assert all(sc[i][ac[i]] == sc[i].max() for i in range(3))
+
+
+def test_long_batched_spectra_take_the_fast_path():
+    """Whole-layer spectra of a long run (notebooks cells 12-13 at BASELINE config 2's step count): 256 series of
+    10 001 samples -- 2.6e10 terms for the direct sum, a few milliseconds for the chirp-z path picked by default."""
+    import time
+
+    n = 10001
+    t = np.arange(n)
+    x = np.sin(0.05 * t)[None, :] * np.linspace(0.5, 2.0, 256)[:, None] + 0.1 * np.cos(0.31 * t)[None, :]
+    t0 = time.perf_counter()
+    s, a = tk.dft_abs(x)
+    wall = time.perf_counter() - t0
+    assert rel_inf(s, np.abs(np.fft.fft(x, axis=1))) < 1e-12
+    assert set(np.minimum(a, n - a).tolist()) == {int(round(0.05 * n / (2 * np.pi)))}
+    assert wall < 5.0
+
+
 def test_run_fft_reference_contract():
     """tests/test_physics.py:30-38 and tests/test_invariants.py:96-115 of the reference."""
     h = tk.SimulationHistory([{0: 0.0}, {0: 1.0}, {0: 0.0}, {0: -1.0}], dt=0.5, wave_speed=1.0)

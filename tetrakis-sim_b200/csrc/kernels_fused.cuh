@@ -26,7 +26,9 @@
 
 namespace tk {
 
-constexpr int kFusedMaxProbes = 8;
+// Probes of a fused run: every CTA filters them down to the ones inside its own tile once (shared memory), so the
+// per-row check costs nothing where there is no probe and the list can be long.
+constexpr int kFusedMaxProbes = 64;
 struct FusedProbes {
     int n;
     int q[kFusedMaxProbes];
@@ -305,6 +307,19 @@ lat_fused2d_kernel(int S, int nrows, int K, T *ua, T *ub, const double *__restri
         if (CROSS) rowresp[i] = (j < 4 ? respR : respRb)[((size_t)(r_begin + rl) * 4 + q) * 2];
         else rowresp[i] = k >= 0 ? respR[((size_t)k * nrows + r_begin + rl) * 4 + q] : 0.0;
     }
+    // probes inside this CTA's tile (rows [r_begin, r_end) x columns [col0, col0 + ncol)): usually none
+    __shared__ int sp_n;
+    __shared__ int sp_idx[kFusedMaxProbes];
+    if (threadIdx.x == 0) {
+        int n = 0;
+        if (!CROSS) {
+            for (int p = 0; p < probes.n; ++p) {
+                const long long pr = probes.cell[p] / S, pc = probes.cell[p] % S;
+                if (pr >= r_begin && pr < r_end && pc >= col0 && pc < col0 + ncol) sp_idx[n++] = p;
+            }
+        }
+        sp_n = n;
+    }
     __syncthreads();
     if (!CROSS) {
         oa = ua;
@@ -345,9 +360,9 @@ lat_fused2d_kernel(int S, int nrows, int K, T *ua, T *ub, const double *__restri
             }
         }
         bool hit = false;
-        if (!CROSS) {
+        if (!CROSS && sp_n > 0) {
 #pragma unroll 1
-            for (int p = 0; p < probes.n; ++p) hit |= valid && probes.cell[p] == (long long)r * S + c0;
+            for (int i = 0; i < sp_n; ++i) hit |= valid && probes.cell[sp_idx[i]] == (long long)r * S + c0;
         }
         // Cell eigenbasis: the cell operator ca*I + coeff*J (J = all-ones 4x4) acts as (ca + 4 coeff) on the
         // cell mean m and as ca on the deviations d_q = u_q - m (d_3 = -(d_0+d_1+d_2)), so K steps are four
@@ -384,13 +399,15 @@ lat_fused2d_kernel(int S, int nrows, int K, T *ua, T *ub, const double *__restri
                 TK_FUSED_STEP();
                 if (hit) {
 #pragma unroll 1
-                    for (int p = 0; p < probes.n; ++p)
+                    for (int i = 0; i < sp_n; ++i) {
+                        const int p = sp_idx[i];
                         if (probes.cell[p] == (long long)r * S + c0) {
                             const int pq = probes.q[p];
                             const double dq = pq == 0 ? d0 : (pq == 1 ? d1 : (pq == 2 ? d2 : -((d0 + d1) + d2)));
                             probe_series[(size_t)(base_row + k) * probes.n + p] =
                                 (m + dq) + (respR[((size_t)k * nrows + r) * 4 + pq] + respC[((size_t)k * S + c0) * 4 + pq]);
                         }
+                    }
                 }
             }
         }

@@ -16,6 +16,7 @@
 
 #include "kernels_cross.cuh"
 #include "kernels_ensemble.cuh"
+#include "kernels_fft.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_graph.cuh"
 #include "kernels_lattice.cuh"

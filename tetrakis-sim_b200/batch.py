@@ -140,7 +140,15 @@ def main(argv=None) -> int:
     metadata["csv_filename"] = csv_filename
     metadata["plot_filename"] = plot_filename
     metadata["run_id"] = run_id
-    metadata["dominant_freq"] = float(freq[np.argmax(spectrum)])
+    # batch.py:205 takes argmax over the two-sided spectrum of a real signal, where bins k and N-k are equal up to
+    # FFT rounding (numpy's own pocketfft picks -0.784 at BASELINE config 1, scipy.fft +0.784: SURVEY.md 0.5).  The
+    # tie is broken towards the lower bin here, so the sign is deterministic: compare |dominant_freq|.
+    k = int(np.argmax(spectrum))
+    mirror = (len(spectrum) - k) % len(spectrum)
+    if mirror < k and abs(spectrum[mirror] - spectrum[k]) <= 1e-9 * abs(spectrum[k]):
+        k = mirror
+    metadata["dominant_freq"] = float(freq[k])
+    metadata["dominant_freq_tie"] = "bins k and N-k of a real signal tie to rounding; the lower bin is reported"
     json_filename = os.path.join(args.outdir, f"{prefix}_metadata.json")
     with open(json_filename, "w") as f:
         json.dump(metadata, f, indent=2)

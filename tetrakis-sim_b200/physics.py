@@ -347,6 +347,12 @@ def run_fft_many(history, nodes, *, dt: float | None = None, device: int = 0):
 
 
 def dominant_frequency(freq, spectrum) -> float:
-    """``float(freq[np.argmax(spectrum)])`` (reference batch.py:205).  The sign is not meaningful
-    for a real signal: bins k and N-k tie up to rounding."""
-    return float(np.asarray(freq)[int(np.argmax(spectrum))])
+    """``float(freq[np.argmax(spectrum)])`` (reference batch.py:205) with the k <-> N-k tie of a real signal's
+    two-sided spectrum (equal up to FFT rounding) broken towards the lower bin, so that the
+    sign does not depend on the FFT implementation."""
+    spectrum = np.asarray(spectrum)
+    k = int(np.argmax(spectrum))
+    mirror = (len(spectrum) - k) % len(spectrum)
+    if mirror < k and abs(spectrum[mirror] - spectrum[k]) <= 1e-9 * abs(spectrum[k]):
+        k = mirror
+    return float(np.asarray(freq)[k])

@@ -257,6 +257,13 @@ int tk_lattice_push_halos(tk_plan *plan, void *cuda_stream);
  * this rank's arrival flags are >= value. */
 int tk_lattice_signal(tk_plan *plan, uint64_t value, void *cuda_stream);
 int tk_lattice_wait(tk_plan *plan, uint64_t value, void *cuda_stream);
+/* Early signal: arm the NEXT tk_lattice_step_layers(plan, 0, all layers) launch to write `value` into the neighbours'
+ * arrival flags itself, as soon as the warps of the first / last owned layer (the only ones that read this rank's halos
+ * and push into the neighbours') have finished -- the boundary layer groups are scheduled first in that launch -- instead
+ * of a stream-ordered write after the whole kernel.  tk_lattice_signal_pending tells whether the launch took the
+ * request (0) or the caller still has to call tk_lattice_signal (1: fp32 plans, split launches, kernel variants). */
+int tk_lattice_arm_signal(tk_plan *plan, uint64_t value);
+int tk_lattice_signal_pending(tk_plan *plan, int32_t *pending);
 /* Device addresses of this plan's two state buffers (for attaching plans of the same process). */
 int tk_lattice_state_ptrs(tk_plan *plan, void **buf0, void **buf1);
 

@@ -28,7 +28,8 @@ ABI_SYMBOLS = (
     "tk_lattice_halo_ptrs", "tk_lattice_step_begin", "tk_lattice_step_layers",
     "tk_lattice_step_layers_on", "tk_lattice_step_end", "tk_lattice_tiling",
     "tk_lattice_ipc_export", "tk_ipc_open", "tk_ipc_close", "tk_lattice_peer_attach",
-    "tk_lattice_set_push_mode", "tk_lattice_push_halos", "tk_lattice_signal", "tk_lattice_wait", "tk_lattice_state_ptrs", "tk_dft_abs", "tk_ensemble_run", "tk_ensemble_run_ex",
+    "tk_lattice_set_push_mode", "tk_lattice_push_halos", "tk_lattice_signal", "tk_lattice_wait",
+    "tk_lattice_arm_signal", "tk_lattice_signal_pending", "tk_lattice_state_ptrs", "tk_dft_abs", "tk_ensemble_run", "tk_ensemble_run_ex",
 )  # fmt: skip
 
 
@@ -132,6 +133,8 @@ def lib():
     L.tk_lattice_push_halos.argtypes = [P, P]
     L.tk_lattice_signal.argtypes = [P, ctypes.c_uint64, P]
     L.tk_lattice_wait.argtypes = [P, ctypes.c_uint64, P]
+    L.tk_lattice_arm_signal.argtypes = [P, ctypes.c_uint64]
+    L.tk_lattice_signal_pending.argtypes = [P, POINTER(c_int32)]
     L.tk_lattice_state_ptrs.argtypes = [P, POINTER(P), POINTER(P)]
     L.tk_lattice_tiling.argtypes = [P, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32),
                                     POINTER(c_int32)]  # fmt: skip
@@ -433,6 +436,15 @@ class Plan:
 
     def signal(self, value: int, cuda_stream: int = 0):
         check(lib().tk_lattice_signal(self._h, int(value), c_void_p(cuda_stream)))
+
+    def arm_signal(self, value: int):
+        """The next step launch over all layers signals ``value`` from inside the kernel (tk_lattice_arm_signal)."""
+        check(lib().tk_lattice_arm_signal(self._h, int(value)))
+
+    def signal_pending(self) -> bool:
+        v = c_int32(0)
+        check(lib().tk_lattice_signal_pending(self._h, ctypes.byref(v)))
+        return bool(v.value)
 
     def wait(self, value: int, cuda_stream: int = 0):
         check(lib().tk_lattice_wait(self._h, int(value), c_void_p(cuda_stream)))

@@ -46,6 +46,16 @@ struct LatDev {
     // pointer (cudaIpc), so the boundary update and the halo exchange are one kernel.
     double *peer_lo;        // lower neighbour's upper-halo plane of the buffer being written, or null
     double *peer_hi;        // upper neighbour's lower-halo plane, or null
+    // Early arrival signal (optional, lat_step_kernel only): the warps that update the first / last owned layer are
+    // the only ones that read this rank's halos and push into the neighbours'; the last of them to finish writes the
+    // step's flag value into the neighbour's arrival flag from inside the kernel (fence + counter), so the neighbour's
+    // stream-ordered wait is satisfied while the interior is still being updated.  The CTAs of the two boundary layer
+    // groups are scheduled first (bnd_first) so that this happens early in the launch.
+    unsigned long long *sig_lo, *sig_hi;  // neighbours' arrival flags (peer-mapped), or null
+    unsigned long long sig_value;
+    unsigned int *sig_cnt;                // local arrival counters: [0] lower side, [32] upper side; zero between launches
+    unsigned int sig_target;              // warps per boundary layer in this launch
+    int bnd_first;
 };
 
 __device__ __forceinline__ unsigned plain_flags(const LatDev &P, int zl)
@@ -165,8 +175,21 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
     constexpr bool KEN = MODE == 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int b = blockIdx.x;
-    const int zg = b % nzg;
-    b /= nzg;
+    int zg;
+    if (K3D && P.bnd_first && nzg >= 3) {  // the two boundary layer groups first, then the interior groups interleaved
+        const int nb2 = 2 * nct * nchunk;
+        if (b < nb2) {
+            zg = (b & 1) ? nzg - 1 : 0;
+            b >>= 1;
+        } else {
+            b -= nb2;
+            zg = 1 + b % (nzg - 2);
+            b /= nzg - 2;
+        }
+    } else {
+        zg = b % nzg;
+        b /= nzg;
+    }
     const int ct = b % nct;
     const int ch = b / nct;
     const int zl = zl_begin + zg * WZ + warp / WC;
@@ -327,6 +350,25 @@ lat_step_kernel(const __grid_constant__ LatDev P, const double *__restrict__ u,
     if (KEN) {
         eacc = warp_sum(eacc);
         if (lane == 0) pen[(size_t)blockIdx.x * 8 + warp] = eacc;
+    }
+    if (K3D && STEP) {  // early arrival signal (see LatDev): warp-uniform conditions
+        const bool lo = zl == 0 && P.sig_lo != nullptr, hi = zl == P.Lloc - 1 && P.sig_hi != nullptr;
+        if (lo || hi) {
+            __threadfence_system();  // this lane's pushes are visible to the neighbour before the count moves
+            __syncwarp();
+            if (lane == 0) {
+                if (lo && atomicAdd(P.sig_cnt, 1u) == P.sig_target - 1) {
+                    __threadfence_system();
+                    atomicExch(P.sig_cnt, 0u);
+                    *reinterpret_cast<volatile unsigned long long *>(P.sig_lo) = P.sig_value;
+                }
+                if (hi && atomicAdd(P.sig_cnt + 32, 1u) == P.sig_target - 1) {
+                    __threadfence_system();
+                    atomicExch(P.sig_cnt + 32, 0u);
+                    *reinterpret_cast<volatile unsigned long long *>(P.sig_hi) = P.sig_value;
+                }
+            }
+        }
     }
 }
 

@@ -238,6 +238,9 @@ struct tk_plan {
     int peer_layers[2] = {0, 0};
     unsigned long long *flags = nullptr;     // this rank's arrival flags: [0] from below, [16] from above
     bool push_in_kernel = true;              // step kernel stores boundary planes into the peers' halos
+    unsigned long long armed_signal = 0;     // != 0: the next full-range step launch signals this value itself
+    unsigned int *sig_cnt = nullptr;         // [64] arrival counters of the early signal (own allocation: the flag
+                                             // block is written by the neighbours over NVLink)
     // CUDA-graph replay of the stepping loop: output rows come from device counters
     long long *ctr_dev = nullptr;            // [0] probe row, [1] history row, [2] energy row
     bool ctr_mode = false;

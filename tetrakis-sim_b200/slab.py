@@ -30,9 +30,9 @@ from .lattice import LatticeSpec
 class _RawCuda:
     """Zero-copy view of library-owned device memory for torch (``__cuda_array_interface__``)."""
 
-    def __init__(self, ptr: int, n_doubles: int):
+    def __init__(self, ptr: int, n: int, typestr: str = "<f8"):
         self.__cuda_array_interface__ = {
-            "shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 3,
+            "shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3,
         }  # fmt: skip
 
 
@@ -52,12 +52,13 @@ class CudaSlabBackend:
 
     def planes(self, next_state: bool):
         p = self.plan.halo_ptrs(next_state)
-        n = p["plane_bytes"] // 8
+        esz, typestr = (4, "<f4") if self.plan.f32 else (8, "<f8")  # fp32 plans exchange fp32 planes
+        n = p["plane_bytes"] // esz
         out = {}
         for k in ("send_lo", "send_hi", "recv_lo", "recv_hi"):
             key = p[k]
             if key not in self._views:
-                self._views[key] = self.torch.as_tensor(_RawCuda(key, n), device=f"cuda:{self.device}")
+                self._views[key] = self.torch.as_tensor(_RawCuda(key, n, typestr), device=f"cuda:{self.device}")
             out[k] = self._views[key]
         return out
 
@@ -89,6 +90,28 @@ class CudaSlabBackend:
         return getattr(self.plan, name)
 
 
+def p2p_possible(dist, rank: int, world: int, device: int) -> bool:
+    """The peer-memory transports need every z-neighbour on the same host and peer-accessible; all ranks must take
+    the same decision.  False => the NCCL transport (multi-node runs, topologies without P2P)."""
+    import socket
+
+    import torch
+
+    where = [None] * world
+    dist.all_gather_object(where, (socket.gethostname(), int(device)))
+    ok = True
+    for nb in (rank - 1, rank + 1):
+        if 0 <= nb < world:
+            host, dev = where[nb]
+            if host != where[rank][0]:
+                ok = False
+            elif dev != device and not torch.cuda.can_device_access_peer(device, dev):
+                ok = False
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{device}")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 class SlabRunner:
     """Steps one rank's slab and exchanges halos with the z-neighbours."""
 
@@ -112,8 +135,18 @@ class SlabRunner:
         self.interior_first = os.environ.get("TK_SLAB_ORDER", "boundary_first") == "interior_first"
         self.split = os.environ.get("TK_SLAB_SPLIT", "0") == "1"
         self.copy_push = False
+        # in-kernel early arrival signal (tk_lattice_arm_signal): measured SLOWER than the plain stream-ordered flag on
+        # 2 x B200 (1.286 vs 1.229 ms per step, profiles/r02_slab_transports.md) -- scheduling the boundary layer groups
+        # first costs their z-neighbours' L2 hits -- so it is opt-in
+        self.early_signal = os.environ.get("TK_SLAB_EARLY", "0") == "1" and hasattr(backend, "arm_signal")
         if self.transport == "p2p-copy":  # peer memory + flags, planes moved by copy engines after the step
             self.transport, self.copy_push = "p2p", True
+        if self.transport == "p2p" and hasattr(backend, "device") and not p2p_possible(dist, rank, world, backend.device):
+            import warnings
+
+            warnings.warn("z-neighbours are not peer-accessible GPUs of one host: falling back to the NCCL transport",
+                          RuntimeWarning, stacklevel=2)
+            self.transport, self.copy_push = "nccl", False
         if self.transport == "p2p":
             backend.attach_peers(dist, rank, world, spec)
             backend.set_push_mode(not self.copy_push)
@@ -249,8 +282,13 @@ class SlabRunner:
             b = self.backend
             st = self.main_stream.cuda_stream
             b.wait(self._push_count, st)
-            b.step_layers(0, self.n_local_layers)
             self._push_count += 1
+            if self.early_signal:  # the kernel itself raises the neighbours' flags once its boundary warps are done
+                b.arm_signal(self._push_count)
+            b.step_layers(0, self.n_local_layers)
+            # ... and the stream-ordered write of the same value follows the kernel in any case: the in-kernel store is
+            # an optimisation (the neighbour may start its next step while this rank's interior is still being
+            # updated), the stream write is the guarantee
             b.signal(self._push_count, st)
             b.step_end()
             return

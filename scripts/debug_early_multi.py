@@ -31,7 +31,12 @@ for rep in range(reps - 1):
     dist.barrier()
     print(f"rank {rank} rep {rep} done", flush=True)
 runner.begin(0.003, 0.0)
-for s in range(40):
+nsteps = int(sys.argv[6]) if len(sys.argv) > 6 else 40
+jit = len(sys.argv) > 7 and sys.argv[7] == "jitter"
+rng = np.random.default_rng(1234 + 17 * rank)
+for s in range(nsteps):
+    if jit and rng.random() < 0.3:
+        time.sleep(float(rng.random()) * 1e-3)
     runner.step()
     if s % sync_every == sync_every - 1:
         torch.cuda.synchronize()

@@ -34,6 +34,8 @@ def _worker(rank, world, port, out, transport, jitter=False, steps=STEPS):
     try:
         spec = tk.LatticeSpec(**SPEC)
         dev = torch.device(f"cuda:{rank}")
+        if jitter or os.environ.get("TK_TEST_OWN_STREAM") == "1":
+            torch.cuda.set_stream(torch.cuda.Stream(dev))  # a stream of its own, as bench.py uses (not the legacy one)
         backend = CudaSlabBackend(spec, *spec.slab(rank, world), device=rank)
         runner = SlabRunner(spec, backend, rank, world, dist,
                             comm_stream=torch.cuda.Stream(dev, priority=-1),
@@ -43,13 +45,17 @@ def _worker(rank, world, port, out, transport, jitter=False, steps=STEPS):
                  spec.index((spec.size - 1, 1, spec.layers - 1, "D")): 0.25}
         mine = {runner.local_index(g): v for g, v in kicks.items() if runner.owns(g)}
         backend.set_state_sparse(list(mine), list(mine.values()))
+        if jitter:  # load the delay kernel now: a first-use module load in the middle of a run of stream-ordered
+            torch.cuda._sleep(1000)  # waits can need the context to drain
+            torch.cuda.synchronize()
+            dist.barrier()
         runner.begin(COEFF, DAMPING)
         rng = np.random.default_rng(1234 + 17 * rank)  # every rank draws its own delays
         for _ in range(steps):
             if jitter:
                 # a rank that runs ahead or falls behind by random amounts: up to ~2 ms of device stall on its
                 # main stream and up to 1 ms of host stall, so flags and halos are produced and consumed out of step
-                if rng.random() < 0.5:
+                if rng.random() < 0.5 and os.environ.get("TK_STRESS_DEVICE_DELAY", "1") == "1":
                     torch.cuda._sleep(int(rng.integers(1, 4_000_000)))
                 if rng.random() < 0.3:
                     time.sleep(float(rng.random()) * 1e-3)

@@ -959,6 +959,35 @@ lat_finalise_kernel(int S, int Lloc, int nsegk, int nchunk, int nrowblk,
     }
 }
 
+// Arrival flags of the halo exchange as kernels (one thread each), the default since round 2: the stream-ordered
+// driver memory operations (cuStreamWriteValue64 / cuStreamWaitValue64) dead-locked under random host-side delays
+// between the ranks (tests/test_gpu_multi.py::test_halo_flag_protocol_survives_random_delays: both GPUs parked in
+// their waits with every operation enqueued) although they never did in lock-step runs.  The wait polls this rank's
+// own flag words with acquire loads -- the neighbour runs on ANOTHER GPU, so nothing on this device has to make
+// progress for the flag to arrive -- and traps after ~20 s instead of hanging the device.
+__global__ void flag_signal_kernel(unsigned long long *f0, unsigned long long *f1, unsigned long long value)
+{
+    __threadfence_system();  // everything this stream did before (the pushes) is visible before the flag moves
+    if (f0) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f0), "l"(value) : "memory");
+    if (f1) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f1), "l"(value) : "memory");
+}
+
+__global__ void flag_wait_kernel(const unsigned long long *f0, const unsigned long long *f1, unsigned long long value)
+{
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; ++side) {
+        const unsigned long long *f = side ? f1 : f0;
+        if (!f) continue;
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= value) break;
+            __nanosleep(100);
+            if (clock64() - t0 > 40000000000LL) __trap();  // ~20 s at 2 GHz: fail loudly, never hang the device
+        }
+    }
+}
+
 // max over existing nodes of the graph degree (reference physics.py:60-64), from the tables.
 __global__ void __launch_bounds__(256)
 lat_maxdeg_kernel(const __grid_constant__ LatDev P, int *__restrict__ out)

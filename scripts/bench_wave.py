@@ -6,7 +6,8 @@ Same flags and the same CSV (header and column meaning, reference scripts/bench_
 effective_dt,stability_adjusted``.  ``build_s`` is the graph-to-device compile, ``sim_s_*`` the wall
 time of ``run_wave_sim`` (kick ``(size//2, size//2[, layers//2], "A")``, bench_wave.py:43-46).
 ``--path graph`` builds the networkx graph (``LatticeSpec.to_networkx``) and runs the bit-exact sliced-ELL
-kernel (sizes networkx can hold); the default ``--path spec`` uses a LatticeSpec and scales to any size.
+kernel (sizes networkx can hold), ``--path graph-structured`` the same graph recognised as a tetrakis lattice and run
+on the structured kernel; the default ``--path spec`` uses a LatticeSpec and scales to any size.
 ``--gnups`` appends node-updates/s columns.
 """
 
@@ -37,7 +38,7 @@ def bench_one(size, dim, layers, steps, c, dt, damping, repeats, path):
     spec = tk.LatticeSpec(size=size, dim=dim, layers=layers)
     kick = spec.bench_kick_node()
     t0 = time.perf_counter()
-    if path == "graph":
+    if path in ("graph", "graph-structured"):
         target = spec.to_networkx()
     else:
         target = spec
@@ -48,7 +49,7 @@ def bench_one(size, dim, layers, steps, c, dt, damping, repeats, path):
         for _ in range(repeats):
             t1 = time.perf_counter()
             hist = tk.run_wave_sim(target, steps=steps, initial_data={kick: 1.0}, c=c, dt=dt, damping=damping,
-                                   final_state=path == "graph")  # the script only reads hist.dt / metadata
+                                   final_state=path != "spec")  # the script only reads hist.dt / metadata
             times.append(time.perf_counter() - t1)
             dts.append(float(hist.dt))
             adjusted = adjusted or bool(hist.metadata.get("stability_adjusted", False))
@@ -70,9 +71,13 @@ def main(argv=None) -> int:
     p.add_argument("--c", type=float, default=1.0)
     p.add_argument("--dt", type=float, default=0.1)
     p.add_argument("--damping", type=float, default=0.0)
-    p.add_argument("--path", choices=["spec", "graph"], default="spec")
+    p.add_argument("--path", choices=["spec", "graph", "graph-structured"], default="spec",
+                   help="graph-structured: the networkx graph, recognised as a tetrakis lattice and run on the "
+                        "structured kernel (what TETRAKIS_B200_AUTO_STRUCTURED=1 / install(structured=True) does)")
     p.add_argument("--gnups", action="store_true", help="append node-updates/s columns")
     a = p.parse_args(argv)
+    if a.path == "graph-structured":
+        os.environ["TETRAKIS_B200_AUTO_STRUCTURED"] = "1"
     sizes = [int(t) for item in a.sizes for t in item.split(",") if t.strip()]
     if not sizes:
         raise SystemExit("No sizes provided.")
@@ -81,7 +86,7 @@ def main(argv=None) -> int:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore", RuntimeWarning)
         wspec = tk.LatticeSpec(size=3, dim=a.dim, layers=2)
-        tk.run_wave_sim(wspec.to_networkx() if a.path == "graph" else wspec, steps=9, dt=a.dt)
+        tk.run_wave_sim(wspec.to_networkx() if a.path != "spec" else wspec, steps=9, dt=a.dt)
     for s in sizes:
         r = bench_one(s, a.dim, a.layers, a.steps, a.c, a.dt, a.damping, a.repeats, a.path)
         line = (f"{r['dim']},{r['layers']},{r['size']},{r['steps']},{r['repeats']},{r['nodes']},{r['edges']},"

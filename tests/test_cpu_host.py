@@ -505,3 +505,75 @@ def test_fused_pass_with_defects_algebra_in_three_dimensions(kw):
             upb, ub = ub, np.where(cross, 0.0, unb)
         u, up = np.where(cross, uc, ub), np.where(cross, upc, upb)
     assert np.abs(u.reshape(-1) - ref["u"]).max() <= 1e-13 * np.abs(ref["u"]).max()
+
+
+@pytest.mark.parametrize("dim,size,layers,kw", [
+    (2, 9, 1, dict(defect="none")),
+    (2, 11, 1, dict(defect="blackhole", radius=2.5)),
+    (2, 10, 1, dict(defect="wedge")),
+    (2, 9, 1, dict(defect="singularity", radius=1.5, mass=50.0, potential=2.0)),
+    (3, 7, 5, dict(defect="blackhole", radius=2.0)),
+    (3, 6, 4, dict(defect="singularity", radius=1.5, mass=2000.0, prune_edges=True)),
+    (3, 7, 3, dict(defect="wedge")),
+])
+def test_graph_read_as_clique_model_plus_exceptions(dim, size, layers, kw):
+    """compiler.lattice_tables_from_graph (the vectorised graph -> structured-kernel route that path="auto" takes when
+    TETRAKIS_B200_AUTO_STRUCTURED=1): the tables it reads off the reference-built graph, run through the oracle's
+    clique-sum restatement, reproduce the oracle's literal per-edge run on the same graph; two hand-made edge edits
+    (one model edge removed, one foreign edge added) come out as exactly four directed corrections."""
+    from oracle import lattice_oracle as lo
+    from oracle import wave_oracle as wo
+    from tetrakis_sim_b200.compiler import lattice_tables_from_graph
+
+    G, removed, center = lo.build_case(size, dim, layers, **kw)
+    t = lattice_tables_from_graph(G)
+    assert (t["size"], t["layers"], t["dim"]) == (size, layers, dim)
+    spec = tk.LatticeSpec(size=size, dim=dim, layers=layers, **kw)
+    si, sf, sm, sv = spec.specials()
+    assert np.array_equal(t["special_index"], np.sort(si)) and sorted(t["corr"]) == sorted(spec.corrections())
+
+    def both(G, t):
+        nodes, rowptr, colidx, inv_mass, potential = lo.graph_arrays(G)
+        deg = np.array([G.degree[v] for v in nodes], dtype=np.float64)
+        u0 = np.zeros(len(nodes))
+        u0[len(nodes) // 2], u0[len(nodes) // 3] = 1.0, -0.4
+        coeff = 0.9 / max(deg.max(), 1.0)
+        ref = wo.run_graph(rowptr, colidx, deg, inv_mass, potential, u0, 30, coeff, 0.01)["history"][-1]
+        n = t["layers"] * t["size"] ** 2 * 4
+        flags, im, pot = np.full(n, 3, np.uint8), np.ones(n), np.zeros(n)
+        flags[t["special_index"]], im[t["special_index"]] = t["special_flags"], t["special_inv_mass"]
+        pot[t["special_index"]] = t["special_potential"]
+        us = np.zeros(n)
+        us[t["state_index"]] = u0
+        got = wo.run_structured(t["size"], t["layers"], flags, im, pot, t["corr"], us, 30, coeff, 0.01)["u"]
+        return np.max(np.abs(got[t["state_index"]] - ref)) / np.max(np.abs(ref))
+
+    assert both(G, t) < 1e-13
+    # hand edits: cut one row-clique edge, add one edge the model does not have
+    q = "A"
+    a, b = ((1, 0, q), (1, 2, q)) if dim == 2 else ((1, 0, 0, q), (1, 2, 0, q))
+    x, y = ((0, 0, "B"), (2, 1, "C")) if dim == 2 else ((0, 0, 0, "B"), (2, 1, 1, "C"))
+    if G.has_edge(a, b) and not G.has_edge(x, y) and G.degree[x] and G.degree[y]:
+        G.remove_edge(a, b)
+        G.add_edge(x, y)
+        t2 = lattice_tables_from_graph(G)
+        assert len(t2["corr"]) == len(t["corr"]) + 4
+        assert sorted(s for _, _, s in t2["corr"])[:2] == [-1.0, -1.0]
+        assert both(G, t2) < 1e-13
+        with pytest.raises(ValueError):
+            lattice_tables_from_graph(G, max_corrections=1)
+
+
+def test_graphs_that_are_not_tetrakis_lattices_are_refused_by_the_structured_route():
+    import networkx as nx
+
+    from tetrakis_sim_b200.compiler import lattice_tables_from_graph
+
+    with pytest.raises(ValueError):
+        lattice_tables_from_graph(nx.path_graph(5))
+    G = nx.Graph()
+    G.add_edge((0, 0, "A"), (0, 0, "A"))  # self-loop
+    with pytest.raises(ValueError):
+        lattice_tables_from_graph(G)
+    with pytest.raises(ValueError):
+        lattice_tables_from_graph(nx.MultiGraph([((0, 0, "A"), (0, 0, "B"))]))

@@ -160,6 +160,44 @@ def _variant_case(cpl, wc, rchunk, case, monkeypatch):
     assert rel_inf(hist.probe_series, ref["probes"]) < 1e-12
 
 
+def test_auto_path_takes_the_structured_kernel_when_opted_in(monkeypatch):
+    """with TETRAKIS_B200_AUTO_STRUCTURED=1 (or install(structured=True)) path="auto" recognises
+    the lattice the reference's front-ends build and runs it on the structured kernel; a graph that is not a tetrakis
+    lattice, and every graph without the opt-in, stays on the bit-exact generic kernel."""
+    import networkx as nx
+
+    from oracle import lattice_oracle as lo
+    from tetrakis_sim_b200 import physics as ph
+
+    G, _, center = lo.build_case(13, 3, 5, "blackhole", radius=2.5)
+    kick = lo.pick_kick_node(G, center, 3)
+    seen = []
+    real = ph.structured_from_graph
+    monkeypatch.setattr(ph, "structured_from_graph", lambda *a, **k: (seen.append(1), real(*a, **k))[1])
+    kw = dict(steps=40, initial_data={kick: 1.0}, dt=0.2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        a = tk.run_wave_sim(G, **kw)
+        assert not seen
+        monkeypatch.setenv("TETRAKIS_B200_AUTO_STRUCTURED", "1")
+        b = tk.run_wave_sim(G, **kw)
+        assert len(seen) == 1
+        assert rel_inf(b.array, a.array) < 1e-12 and a.metadata == b.metadata and list(b[7]) == list(a[7])
+        # not a lattice: falls back to the generic kernel without an error
+        H = nx.barabasi_albert_graph(200, 3, seed=1)
+        h1 = tk.run_wave_sim(H, steps=10, dt=0.05)
+        monkeypatch.delenv("TETRAKIS_B200_AUTO_STRUCTURED")
+        h0 = tk.run_wave_sim(H, steps=10, dt=0.05)
+        assert np.array_equal(h0.array, h1.array)
+        # install(structured=True) is the same switch
+        ph.set_auto_structured(True)
+        try:
+            c = tk.run_wave_sim(G, **kw)
+        finally:
+            ph.set_auto_structured(None)
+        assert len(seen) == 3 and np.array_equal(c.array, b.array)
+
+
 def test_structured_and_graph_kernels_agree_on_a_medium_singularity_lattice():
     """SURVEY.md 8d config 4 cross-check: structured vs sliced-ELL on the same operator."""
     from oracle import lattice_oracle as lo

@@ -169,60 +169,109 @@ def detect_lattice_shape(G):
     return dim, max(rmax, cmax) + 1, (zmax + 1 if dim == 3 else 1)
 
 
-def structured_from_graph(G, shape=None, device: int = 0) -> CompiledGraph:
-    """Route a tetrakis-shaped ``networkx`` graph to the structured kernel.
+def lattice_tables_from_graph(G, shape=None, max_corrections: int | None = None) -> dict:
+    """Read a tetrakis-shaped ``networkx`` graph as "clique model + sparse exceptions" -- host only, NumPy only.
 
-    O(E) host work (it enumerates the model's edges to diff them against G), so this is for
-    graphs networkx can hold anyway."""
+    The structured kernel evaluates the operator of ``tetrakis_sim/lattice.py:30-73`` (cell, row and column cliques,
+    vertical links) from per-node bits: ``alive`` (the node exists) and ``part`` (it has edges).  Everything else the
+    graph says becomes explicit data: nodes that are missing (black hole, ``defects.py:110-135``), nodes without
+    edges (``prune_edges``, ``defects.py:231-238``), ``mass`` / ``potential`` attributes (``defects.py:221-229``), and
+    one directed correction ``(a, b, +-1)`` for every edge on which graph and model differ (the wedge cut,
+    ``defects.py:80-84``; any edge a caller added or removed by hand).
+
+    Cost: one C-level pass over the adjacency (``graph_arrays``) + O(E) array arithmetic; model edges the graph lacks
+    are enumerated only around the nodes whose model degree is not met.  Raises ``ValueError`` when the graph is not
+    a tetrakis lattice in this sense (foreign node labels, self-loops, multigraph / directed, or more than
+    ``max_corrections`` exceptions) -- ``path="auto"`` then stays on the generic kernel."""
     shape = shape or detect_lattice_shape(G)
     if shape is None:
         raise ValueError("graph nodes are not tetrakis (r, c[, z], q) tuples")
+    if G.is_multigraph() or G.is_directed():
+        raise ValueError("multigraphs / directed graphs take the generic kernel")
     dim, S, L = shape
-    spec = LatticeSpec(size=S, dim=dim, layers=L)
-    nodes = list(G.nodes)
-    index = {n: i for i, n in enumerate(nodes)}
-    gidx = np.fromiter((spec.index(n) for n in nodes), dtype=np.int64, count=len(nodes))
-    deg_map = dict(G.degree(nodes))
-    alive = np.zeros(spec.num_slots, dtype=bool)
-    part = np.zeros(spec.num_slots, dtype=bool)
-    inv_mass = np.ones(spec.num_slots)
-    potential = np.zeros(spec.num_slots)
-    for n, gi in zip(nodes, gidx):
-        alive[gi] = True
-        part[gi] = deg_map[n] > 0
-        a = G.nodes[n]
-        if a:
-            m = float(a.get("mass", 1.0))
-            inv_mass[gi] = 1.0 / (m if m > 0.0 else 1.0)
-            potential[gi] = float(a.get("potential", 0.0))
+    nodes, index, rowptr, colidx, degree, inv_mass_g, potential_g = graph_arrays(G)
+    n = len(nodes)
+    nslots = L * S * S * 4
+    qmap = {q: i for i, q in enumerate(QUADRANTS)}
+    if dim == 2:
+        coords = np.array([(0, v[0], v[1], qmap[v[2]]) for v in nodes], dtype=np.int64).reshape(-1, 4)
+    else:
+        coords = np.array([(v[2], v[0], v[1], qmap[v[3]]) for v in nodes], dtype=np.int64).reshape(-1, 4)
+    gidx = ((coords[:, 0] * S + coords[:, 1]) * S + coords[:, 2]) * 4 + coords[:, 3]
+    counts = np.diff(rowptr)
+    rows = np.repeat(np.arange(n, dtype=np.int64), counts)
+    if np.any(colidx == rows):
+        raise ValueError("self-loops take the generic kernel")
+    alive = np.zeros(nslots, dtype=bool)
+    part = np.zeros(nslots, dtype=bool)
+    alive[gidx] = True
+    part[gidx] = counts > 0
+    inv_mass = np.ones(nslots)
+    potential = np.zeros(nslots)
+    inv_mass[gidx] = inv_mass_g
+    potential[gidx] = potential_g
     sp = np.flatnonzero(~(alive & part) | (inv_mass != 1.0) | (potential != 0.0))
     flags = (alive[sp] * FLAG_ALIVE + part[sp] * FLAG_PART).astype(np.uint8)
-    # model edges vs graph edges
-    P4 = part.reshape(L, S, S, 4)
-    model = set()
-    plane = S * S * 4
-    for z, r, c, q in zip(*np.nonzero(P4)):
-        a = ((z * S + r) * S + c) * 4 + q
-        for q2 in range(q + 1, 4):
-            if P4[z, r, c, q2]:
-                model.add((a, a - q + q2))
-        for c2 in np.flatnonzero(P4[z, r, c + 1 :, q]):
-            model.add((a, a + (int(c2) + 1) * 4))
-        for r2 in np.flatnonzero(P4[z, r + 1 :, c, q]):
-            model.add((a, a + (int(r2) + 1) * S * 4))
-        if z + 1 < L and P4[z + 1, r, c, q]:
-            model.add((a, a + plane))
-    graph = set()
-    for a, b in G.edges:
-        ia, ib = int(gidx[index[a]]), int(gidx[index[b]])
-        graph.add((min(ia, ib), max(ia, ib)))
-    corr = []
-    for a, b in sorted(model - graph):
-        corr += [(int(a), int(b), -1.0), (int(b), int(a), -1.0)]
-    for a, b in sorted(graph - model):
-        corr += [(a, b, 1.0), (b, a, 1.0)]
-    plan = Plan.lattice(S, L, special_index=sp, special_flags=flags,
-                        special_inv_mass=inv_mass[sp], special_potential=potential[sp], corr=corr,
-                        device=device)  # fmt: skip
-    max_degree = max(deg_map.values(), default=0)
-    return CompiledGraph(plan, nodes, index, int(max_degree), state_index=gidx)
+
+    # ---- graph edges the model does not have: every directed CSR entry, classified at once
+    src, dst = gidx[rows], gidx[colidx]
+    cs, cd = src >> 2, dst >> 2
+    same_q = (src & 3) == (dst & 3)
+    cols, cold = cs % S, cd % S
+    rs_, rd_ = (cs // S) % S, (cd // S) % S
+    zs, zd = cs // (S * S), cd // (S * S)
+    in_model = (cs == cd) | (same_q & (zs == zd) & ((rs_ == rd_) | (cols == cold))) | \
+               (same_q & (rs_ == rd_) & (cols == cold) & (np.abs(zs - zd) == 1))
+    extra = np.flatnonzero(~in_model)
+    corr_a, corr_b, corr_s = [src[extra]], [dst[extra]], [np.ones(extra.size)]
+
+    # ---- model edges the graph does not have: only around nodes whose model degree is not met
+    P4 = part.reshape(L, S, S, 4).astype(np.int64)
+    Pz = np.zeros((L + 2, S, S, 4), dtype=np.int64)
+    Pz[1:-1] = P4
+    model_deg = P4 * ((P4.sum(3, keepdims=True) - 1) + (P4.sum(2, keepdims=True) - 1) +
+                      (P4.sum(1, keepdims=True) - 1) + Pz[:-2] + Pz[2:])
+    met = np.bincount(src[in_model], minlength=nslots)
+    short = np.flatnonzero(model_deg.ravel() != met)
+    if max_corrections is not None and short.size > max_corrections:
+        raise ValueError(f"{short.size} nodes differ from the clique model (limit {max_corrections})")
+    if short.size:
+        row_of_slot = np.full(nslots, -1, dtype=np.int64)
+        row_of_slot[gidx] = np.arange(n)
+        plane = S * S * 4
+        for a in short.tolist():
+            q, cell = a & 3, a >> 2
+            c0, r0, z0 = cell % S, (cell // S) % S, cell // (S * S)
+            cand = [(cell << 2) + np.array([x for x in range(4) if x != q], dtype=np.int64),
+                    (((z0 * S + r0) * S + np.delete(np.arange(S), c0)) << 2) + q,
+                    (((z0 * S + np.delete(np.arange(S), r0)) * S + c0) << 2) + q]
+            if z0 > 0:
+                cand.append(np.array([a - plane], dtype=np.int64))
+            if z0 < L - 1:
+                cand.append(np.array([a + plane], dtype=np.int64))
+            cand = np.concatenate(cand)
+            cand = cand[part[cand]]
+            g = row_of_slot[a]
+            have = dst[rowptr[g]:rowptr[g + 1]]
+            missing = np.setdiff1d(cand, have, assume_unique=True)
+            corr_a.append(np.full(missing.size, a, dtype=np.int64))
+            corr_b.append(missing)
+            corr_s.append(-np.ones(missing.size))
+    corr_a, corr_b, corr_s = np.concatenate(corr_a), np.concatenate(corr_b), np.concatenate(corr_s)
+    if max_corrections is not None and corr_a.size > max_corrections:
+        raise ValueError(f"{corr_a.size} edge corrections against the clique model (limit {max_corrections})")
+    order = np.lexsort((corr_b, corr_a))
+    corr = [(int(a), int(b), float(s)) for a, b, s in zip(corr_a[order], corr_b[order], corr_s[order])]
+    return {"size": S, "layers": L, "dim": dim, "nodes": nodes, "index": index, "state_index": gidx,
+            "special_index": sp, "special_flags": flags, "special_inv_mass": inv_mass[sp],
+            "special_potential": potential[sp], "corr": corr, "max_degree": int(degree.max()) if n else 0}
+
+
+def structured_from_graph(G, shape=None, device: int = 0, max_corrections: int | None = None) -> CompiledGraph:
+    """Route a tetrakis-shaped ``networkx`` graph to the structured kernel (24 bytes per node update instead of
+    44 + 4 * degree): :func:`lattice_tables_from_graph` + ``tk_lattice_plan_create``."""
+    t = lattice_tables_from_graph(G, shape, max_corrections=max_corrections)
+    plan = Plan.lattice(t["size"], t["layers"], special_index=t["special_index"], special_flags=t["special_flags"],
+                        special_inv_mass=t["special_inv_mass"], special_potential=t["special_potential"],
+                        corr=t["corr"], device=device)  # fmt: skip
+    return CompiledGraph(plan, t["nodes"], t["index"], t["max_degree"], state_index=t["state_index"])

@@ -60,6 +60,9 @@ def _spec_key(s: LatticeSpec):
 def mask_arrays(spec: LatticeSpec, want_degrees: bool = False):
     """(cell_bits[L*S*S] uint8, exceptions (node, inv_mass, potential), corrections, max_degree,
     surviving node count) of one lattice+defect -- the per-mask inputs of ``tk_ensemble_run``."""
+    ck = ("mask_arrays", bool(want_degrees))
+    if ck in spec._cache:  # a sweep is usually run more than once over the same specs
+        return spec._cache[ck]
     S, L = spec.size, spec.layers
     alive = np.ones(spec.num_slots, dtype=bool)
     part = np.ones(spec.num_slots, dtype=bool)
@@ -82,9 +85,10 @@ def mask_arrays(spec: LatticeSpec, want_degrees: bool = False):
     max_degree = int(deg[alive].max()) if alive.any() else 0
     keep = alive[idx] & ((im != 1.0) | (pot != 0.0))
     exc = (idx[keep].astype(np.int32), im[keep], pot[keep])
-    if want_degrees:
-        return bits, exc, corr, max_degree, int(alive.sum()), deg, alive
-    return bits, exc, corr, max_degree, int(alive.sum())
+    out = (bits, exc, corr, max_degree, int(alive.sum()), deg, alive) if want_degrees else \
+          (bits, exc, corr, max_degree, int(alive.sum()))
+    spec._cache[ck] = out
+    return out
 
 
 def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, device: int = 0,
@@ -99,8 +103,15 @@ def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, devi
     n = len(specs)
     if n == 0:
         raise ValueError("no simulations")
+    # sweeps hold a few distinct LatticeSpec objects referenced many times (sweep_grid: 64 specs for 65 536
+    # simulations): everything per-spec is done once per OBJECT, the per-simulation part is array indexing
+    sid = list(map(id, specs))
+    distinct: dict = {}
+    for k, s in zip(sid, specs):
+        if k not in distinct:
+            distinct[k] = s
     S, L, dim = specs[0].size, specs[0].layers, specs[0].dim
-    if any((s.size, s.layers, s.dim) != (S, L, dim) for s in specs):
+    if any((s.size, s.layers, s.dim) != (S, L, dim) for s in distinct.values()):
         raise ValueError("all simulations of an ensemble must share the lattice shape")
     c = np.broadcast_to(np.asarray(c, dtype=np.float64), (n,))
     dt = np.broadcast_to(np.asarray(dt, dtype=np.float64), (n,))
@@ -108,23 +119,32 @@ def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, devi
 
     masks: dict = {}
     mask_data = []
-    sim_mask = np.empty(n, dtype=np.int32)
-    sim_kick = np.empty(n, dtype=np.int32)
-    kick_nodes = []
-    kick_cache: dict = {}
-    for i, s in enumerate(specs):
-        k = _spec_key(s)
-        if k not in masks:
-            masks[k] = len(mask_data)
+    mask_kick = []  # per mask: (kick node by the batch.py rule, its index)
+    obj_mask = {}
+    for k, s in distinct.items():
+        key = _spec_key(s)
+        if key not in masks:
+            masks[key] = len(mask_data)
             mask_data.append(mask_arrays(s))
-            kick_cache[k] = s.kick_node()
-        sim_mask[i] = masks[k]
-        node = kicks[i] if kicks is not None else kick_cache[k]
-        if not s.contains(node):
-            raise ValueError(f"kick node {node} is not in the graph after defect application")
-        kick_nodes.append(node)
-        sim_kick[i] = s.index(node)
-    maxdeg = np.array([mask_data[m][3] for m in sim_mask], dtype=np.int64)
+            node = s.kick_node() if kicks is None else None
+            if node is not None and not s.contains(node):
+                raise ValueError(f"kick node {node} is not in the graph after defect application")
+            mask_kick.append((node, s.index(node) if node is not None else -1))
+        obj_mask[k] = masks[key]
+    sim_mask = np.fromiter(map(obj_mask.__getitem__, sid), dtype=np.int32, count=n)
+    if kicks is None:
+        sim_kick = np.array([i for _, i in mask_kick], dtype=np.int32)[sim_mask]
+        kick_nodes = list(map([nd for nd, _ in mask_kick].__getitem__, sim_mask.tolist()))
+    else:
+        sim_kick = np.empty(n, dtype=np.int32)
+        kick_nodes = []
+        for i, s in enumerate(specs):
+            node = kicks[i]
+            if not s.contains(node):
+                raise ValueError(f"kick node {node} is not in the graph after defect application")
+            kick_nodes.append(node)
+            sim_kick[i] = s.index(node)
+    maxdeg = np.array([m[3] for m in mask_data], dtype=np.int64)[sim_mask]
     # physics.py:74-91 per simulation
     eff = dt.astype(np.float64).copy()
     limit = np.where(maxdeg > 0, 1.0 / np.sqrt(np.maximum(maxdeg, 1)), np.inf)
@@ -163,7 +183,7 @@ def run_ensemble(specs, steps: int, c=1.0, dt=0.2, damping=0.0, kicks=None, devi
         freq = np.fft.fftfreq(nt)[arg] / eff  # fftfreq(nt, d=dt)[k] == fftfreq(nt)[k] / dt
     else:
         freq = None
-    updates = int(sum(mask_data[m][4] for m in sim_mask)) * int(steps)
+    updates = int(np.array([m[4] for m in mask_data], dtype=np.int64)[sim_mask].sum()) * int(steps)
     res = EnsembleResult(series, spec_out, arg, freq, eff, clamp, maxdeg, kick_nodes, ms.value, updates, feat)
     res.nt = nt
     return res

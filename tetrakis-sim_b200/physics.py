@@ -10,7 +10,9 @@ Extra keyword-only arguments (all optional; the positional signature is the refe
   device   CUDA device ordinal (default 0)
   path     "auto" | "graph" | "structured".  "graph" is the sliced-ELL kernel that reproduces the
            reference bit for bit on any networkx graph; "structured" the clique-sum kernel
-           (always used for a LatticeSpec).  "auto" = graph for networkx input.
+           (always used for a LatticeSpec).  "auto" = graph for networkx input, unless
+           TETRAKIS_B200_AUTO_STRUCTURED=1 / install(structured=True) opts tetrakis-shaped graphs into the
+           structured kernel (compiler.lattice_tables_from_graph; <= 1e-12 instead of bit-identical).
   reorder  graph path only: device row order, "auto" (default) | "none" | "degree" | "rcm"; never
            changes results (the neighbour order inside a row is kept)
   record   "all" (default for graphs: every state, as the reference returns) or "probes"
@@ -140,12 +142,39 @@ def _cfl(max_degree: int, c: float, dt: float, steps, damping: float):
     return effective_dt, metadata
 
 
+_AUTO_STRUCTURED = None  # None: follow the environment; True / False: set by install(structured=...)
+
+
+def auto_structured_enabled() -> bool:
+    """Does ``path="auto"`` route tetrakis-shaped ``networkx`` graphs to the structured kernel?  Off by default
+    (the generic kernel is bit-identical to the reference); on with ``TETRAKIS_B200_AUTO_STRUCTURED=1`` or
+    ``install(structured=True)``."""
+    import os
+
+    if _AUTO_STRUCTURED is not None:
+        return bool(_AUTO_STRUCTURED)
+    return os.environ.get("TETRAKIS_B200_AUTO_STRUCTURED", "0") == "1"
+
+
+def set_auto_structured(flag) -> None:
+    global _AUTO_STRUCTURED
+    _AUTO_STRUCTURED = flag
+
+
 def _run_graph(G, steps, initial_data, c, dt, damping, device, path, record, probes, energy, reorder="auto",
                steps_requested=None):
-    comp: CompiledGraph
+    comp: CompiledGraph | None = None
     if path == "structured":
         comp = structured_from_graph(G, device=device)
-    else:
+    elif path == "auto" and auto_structured_enabled():
+        # opt-in (TETRAKIS_B200_AUTO_STRUCTURED=1 / install(structured=True)): a graph that IS a tetrakis lattice, up to
+        # a sparse set of exceptions, takes the structured kernel (24 B per update instead of 44 + 4 * degree; results
+        # within 1e-12 of the reference instead of bit-identical); anything else stays on the generic kernel
+        try:
+            comp = structured_from_graph(G, device=device, max_corrections=max(64, G.number_of_edges() // 50))
+        except ValueError:
+            comp = None
+    if comp is None:
         comp = compile_graph(G, device=device, reorder=reorder)
     try:
         nodes, index = comp.nodes, comp.index

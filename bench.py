@@ -63,9 +63,12 @@ def ncu_traffic(workload, k=0):
     A capture of a K-step pass kernel only counts for a run with the same K."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            e = json.load(f)[workload]
+            t = json.load(f)
+        e = t[workload]
         if k and int(e.get("steps_per_pass", k)) != int(k):
-            return None
+            e = t.get(f"{workload}-k{int(k)}")  # a capture at another K, if one was taken
+            if e is None:
+                return None
         return float(e["bytes"])
     except Exception:
         return None
@@ -411,7 +414,10 @@ def bench_lattice(workload, args, local=0, dist=None, steps=None, warmup=None, s
         "e2e": e2e, "gpu_launches": launches,
         # sum_i u_t(i) = 1 + t for unit masses (zero column sums of the Laplacian): a whole-lattice checksum
         "checksum_sum_u": checksum,
-        "checksum_expected": float(steps_done + 1) if spec.defect != "singularity" else None,
+        # (tagged nodes with prune_edges have no edges and stay at rest, so the law also holds for cfg4; tagged nodes
+        # that keep their edges conserve sum_i m_i u_i instead)
+        "checksum_expected": float(steps_done + 1) if (spec.defect != "singularity" or
+                                                       (spec.prune_edges and spec.potential == 0.0)) else None,
     }
 
 

@@ -289,16 +289,27 @@ def bench_sheet(args, emit: bool = True, keep_pg: bool = False):
     if world > 1:
         dist.all_reduce(cs)
 
+    # e2e with host buffers, as at N = 1 (bench.py:bench_lattice): kick H2D, the steps, the kick node's time series D2H
+    # and its |DFT| + dominant bin on the rank that owns the node; "with_final_state" adds every band's D2H
     fence()
     t0 = time.perf_counter()
     backend.set_state_sparse(*kicks)
+    if kicks[0]:
+        backend.set_probes(kicks[0], args.steps + 1)
     runner.run(args.steps, coeff, 0.0, kmax)
+    probe_bytes = 0
+    if kicks[0]:
+        ser = backend.read_probes(args.steps + 1)
+        spectrum, _ = _lib.dft_abs(np.ascontiguousarray(ser[:, 0]), device=local)
+        probe_bytes = ser.nbytes + spectrum.nbytes + 8
+    fence()
+    t1 = time.perf_counter()
     _lib.check(_lib.lib().tk_plan_get_state(backend.plan._h, _lib._p(final), None))
     fence()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor([t1 - t0, time.perf_counter() - t0, float(probe_bytes)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t.item())
+    e2e_probe_s, e2e_s, probe_bytes = (float(x) for x in e2e_t.tolist())
     passes = pass_lengths(args.steps, kmax)
     peak, peak_src = measured_peak_gbs()
     line = None
@@ -323,9 +334,14 @@ def bench_sheet(args, emit: bool = True, keep_pg: bool = False):
                          "kernel_ms_per_launch": kms / max(kpasses, 1),
                          "kernel_share_of_step": kms / ms, "frac_of_8TBs_nominal": achieved / 8000.0},
             "cpu_baseline": None,
-            "e2e": {"value": n_updates * args.steps / e2e_s / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": 16.0 / args.steps,
-                    "d2h_bytes_per_step": world * final.nbytes / args.steps, "seconds": e2e_s},
+            "e2e": {"value": n_updates * args.steps / e2e_probe_s / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": (16.0 + probe_bytes / 2) / args.steps,
+                    "d2h_bytes_per_step": probe_bytes / args.steps, "seconds": e2e_probe_s,
+                    "includes": "kick H2D + run (all ranks, all-reduce per pass) + the kick node's series D2H, its "
+                                "|DFT| and dominant bin (tk_dft_abs) on the owning rank; slowest rank",
+                    "with_final_state": {"value": n_updates * args.steps / e2e_s / 1e9, "seconds": e2e_s,
+                                         "d2h_bytes_per_step": (world * final.nbytes + probe_bytes) / args.steps,
+                                         "includes": "the above + every band's final state D2H into pinned memory"}},
             "gpu_launches": launches, "clocks": clk.summary(),
             "timing": {"repeats": len(reps), "median_ms": ms, "min_ms": min(reps), "max_ms": max(reps),
                        "rule": "the steps-step region repeated until >= 50 ms and >= 5 repeats; value from the median; "

@@ -553,13 +553,24 @@ def bench_slabs(args, emit: bool = True, keep_pg: bool = False):
     dist.barrier()
     t0 = time.perf_counter()
     backend.set_state_sparse(*kicks)
+    if kicks[0]:
+        backend.set_probes(kicks[0], args.steps + 1)
     run(args.steps)
+    probe_bytes = 0
+    if kicks[0]:  # the kick node's time series D2H, its |DFT| and dominant bin on the rank that owns the node
+        ser = backend.read_probes(args.steps + 1)
+        spectrum, _ = _lib.dft_abs(np.ascontiguousarray(ser[:, 0]), device=local)
+        probe_bytes = ser.nbytes + spectrum.nbytes + 8
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.perf_counter()
     _lib.check(_lib.lib().tk_plan_get_state(backend.plan._h, _lib._p(final), None))
     torch.cuda.synchronize()
     dist.barrier()
-    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_t = torch.tensor([t1 - t0, time.perf_counter() - t0, float(probe_bytes)], dtype=torch.float64, device=dev)
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t.item())
+    e2e_probe_s, e2e_s, probe_bytes = (float(x) for x in e2e_t.tolist())
+    backend.set_probes([], 0)
 
     # roofline of the step kernel on this rank's slab, no communication (rank 0 reports)
     backend.set_state_sparse(*kicks)
@@ -595,9 +606,14 @@ def bench_slabs(args, emit: bool = True, keep_pg: bool = False):
                          "kernel": "lat_step_kernel (one slab, no communication)",
                          "bytes_per_update": BYTES_PER_UPDATE, "kernel_ms_per_launch": kms},
             "cpu_baseline": None,
-            "e2e": {"value": n_updates * args.steps / e2e_s / 1e9, "unit": UNIT,
-                    "h2d_bytes_per_step": 16.0 / args.steps,
-                    "d2h_bytes_per_step": world * final.nbytes / args.steps, "seconds": e2e_s},
+            "e2e": {"value": n_updates * args.steps / e2e_probe_s / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": (16.0 + probe_bytes / 2) / args.steps,
+                    "d2h_bytes_per_step": probe_bytes / args.steps, "seconds": e2e_probe_s,
+                    "includes": "kick H2D + run (all ranks, halo exchange per step) + the kick node's series D2H, its "
+                                "|DFT| and dominant bin (tk_dft_abs) on the owning rank; slowest rank",
+                    "with_final_state": {"value": n_updates * args.steps / e2e_s / 1e9, "seconds": e2e_s,
+                                         "d2h_bytes_per_step": (world * final.nbytes + probe_bytes) / args.steps,
+                                         "includes": "the above + every slab's final state D2H into pinned memory"}},
             "gpu_launches": launches, "clocks": clk.summary(),
             "host_enqueue_ms_per_step": 1e3 * host_enqueue_s / args.steps, "slab_mode": mode,
             # the same 64-layer slab on one GPU with no neighbours (rank 0, measured in this run): the

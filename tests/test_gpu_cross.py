@@ -151,6 +151,40 @@ def test_fused_passes_equal_the_step_by_step_kernel_on_a_medium_lattice(monkeypa
     assert np.all(b.final_state[spec.specials()[0]] == 0.0)  # removed nodes stay exactly zero
 
 
+@pytest.mark.parametrize("name,kw", [
+    ("cfg4", dict(size=512, dim=3, layers=512, defect="singularity", radius=2.5, mass=2000.0, prune_edges=True)),
+    ("cfg3-slab", dict(size=1024, dim=3, layers=64, defect="blackhole", radius=64.0)),
+])
+def test_full_size_lattices_in_fused_passes_against_the_step_by_step_kernel(name, kw):
+    """BASELINE configs[3] whole (512^3 singularity, pruned edges: 537 M nodes) and the per-GPU slab of configs[2]
+    (1024^2 x 64, black hole r = 64): four K = 16 passes of the cross scheme against 64 single steps of lat_step_kernel
+    (itself oracle-checked at every size the oracle finishes) -- every final value and two probe series -- plus
+    sum_i u_t(i) = 1 + t and removed / pruned nodes exactly at rest."""
+    spec = tk.LatticeSpec(**kw)
+    steps = 64
+    kick = spec.index(spec.kick_node())
+    far = spec.index((3, spec.size - 5, spec.layers - 2, "D"))
+    plan = tk.compile_lattice(spec)
+    try:
+        dt = min(0.1, 1.0 / np.sqrt(plan.max_degree))
+        coeff = dt * dt
+        plan.set_state_sparse([kick], [1.0])
+        a = plan.run(steps, coeff, 0.0, probes=[kick, far])
+        assert plan.cross["steps_per_pass"] == 16 and plan.fused["fused_steps"] == steps, (plan.cross, plan.fused)
+        ua = plan.get_state()
+        plan.set_state_sparse([kick], [1.0])
+        b = plan.run(steps, coeff, 0.0, probes=[kick, far], fuse=False)
+        ub = plan.get_state()
+    finally:
+        plan.close()
+    assert rel_inf(a["probes"], b["probes"]) < 1e-12
+    scale = float(np.max(np.abs(ub)))
+    ua -= ub
+    assert float(np.max(np.abs(ua))) < 1e-12 * scale
+    assert abs(float(ub.sum()) - (steps + 1.0)) < 1e-9 * (steps + 1.0)
+    assert np.all(ub[spec.specials()[0]] == 0.0)
+
+
 def test_the_cross_scheme_is_not_used_where_it_does_not_apply(monkeypatch):
     monkeypatch.setenv("TK_LAT_FUSE", "8")
     spec = tk.LatticeSpec(size=24, dim=3, layers=6, **DEFECTS["blackhole"])

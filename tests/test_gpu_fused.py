@@ -174,6 +174,46 @@ def test_full_size_config_2_sheet_against_the_oracle():
     assert abs(hist.final_state.sum() - (1.0 + steps)) < 1e-8  # sum_i u_t(i) = 1 + t
 
 
+def test_config_2_at_full_size_and_full_step_count_by_properties():
+    """BASELINE configs[1] whole: 8192^2 nodes AND 10 000 steps (no CPU oracle finishes that: 2.7e12 node updates), checked
+    through properties that hold at any size --
+      (i)  sum_i u_t(i) = 1 + t after the 10 000 steps (zero column sums of the Laplacian, u_{-1} = 0);
+      (ii) time reversal: with (u, u_prev) swapped, 10 000 more steps retrace the trajectory back to the unit kick
+           (the leapfrog map is exactly reversible in exact arithmetic, so what is left is 20 000 steps of rounding);
+      (iii) the kick node's series is the same as on the step-by-step kernel for the first 96 steps (the oracle-checked
+            range of test_full_size_config_2_sheet_against_the_oracle) -- recorded inside the long run."""
+    S, steps = 8192, 10_000
+    spec = tk.LatticeSpec(size=S, dim=2)
+    kick = spec.index(spec.bench_kick_node())
+    dt = min(0.1, 1.0 / np.sqrt(2 * S + 1))  # physics.py:74-80 clamp
+    coeff = dt * dt
+    plan = tk.compile_lattice(spec)
+    try:
+        plan.set_state_sparse([kick], [1.0])
+        out = plan.run(steps, coeff, 0.0, probes=[kick])
+        assert plan.fused["steps_per_pass"] == 48 and plan.fused["fused_steps"] == steps, plan.fused
+        u, up = plan.get_state(want_prev=True)
+        total = float(u.sum())
+        assert abs(total - (steps + 1.0)) < 1e-8 * (steps + 1.0), total
+        assert np.isfinite(u).all() and np.max(np.abs(u)) <= 1.0 + 1e-9  # marginally stable dt: no growth
+        plan.set_state(up, u)
+        del u, up
+        plan.run(steps, coeff, 0.0)
+        back, back_prev = plan.get_state(want_prev=True)
+        assert back_prev[kick] == pytest.approx(1.0, abs=1e-7)
+        back_prev[kick] -= 1.0
+        err = max(float(np.max(np.abs(back))), float(np.max(np.abs(back_prev))))
+        print(f"cfg2 full size, 2 x {steps} steps: sum(u) - (1 + t) = {total - (steps + 1.0):.3e}, time-reversal "
+              f"residual {err:.3e}")
+        assert err < 1e-7, err
+        del back, back_prev
+        plan.set_state_sparse([kick], [1.0])  # zeroes both time levels first
+        ref = plan.run(96, coeff, 0.0, probes=[kick], fuse=False)
+    finally:
+        plan.close()
+    assert rel_inf(out["probes"][:97], ref["probes"]) < 1e-12
+
+
 def test_fused_passes_record_eight_probes_sharing_cells_rows_and_warps():
     """Probes in one cell (all four quadrants), the same node twice, neighbours in one warp segment, first and
     last row: the pass records each from the lane that owns its cell."""

@@ -147,8 +147,8 @@ __device__ __forceinline__ void fx_lines_advance(const FxDev &X, const FxLines &
 // The first `nadv` blocks of the grid do not step cells: they advance the bulk parts and the responses of the lines
 // (fx_lines_advance), which depends on the same line sums and nothing else -- ~200 MB of streaming that hides behind
 // the latency-bound cell update instead of running as a launch of its own.
-template <int MODE>
-__global__ void __launch_bounds__(256, 2)
+template <int MODE, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB)
 fx_cross_step_kernel(const __grid_constant__ LatDev P, const __grid_constant__ FxDev X,
                      const __grid_constant__ FxLines A, const double *__restrict__ u, double *__restrict__ w,
                      double coeff, double damping, long long ntaskR, long long ntaskC, int nadv)

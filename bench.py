@@ -488,6 +488,8 @@ def default_extras(args, local):
                                             "roofline_frac": r1["roofline"]["frac"]}
     other["cfg5-ensemble"] = ensemble_short(local)
     other["cfg1-batch"] = cfg1_short(local, cpu=not args.no_cpu)
+    if not args.no_cpu:
+        other["cpu_reference_tables"] = cpu_reference_tables(local)
     out["other_configs"] = other
     return out
 
@@ -574,6 +576,96 @@ def cfg1_short(local, cpu=True):
         out["cpu_literal_1_core"] = cpu_literal_cfg1()
     out["reference_python_networkx_s"] = 0.593  # SURVEY.md section 3a, measured on this image's host
     return out
+
+
+def _literal_inputs(spec):
+    """CSR + attributes of the reference-built graph of ``spec`` (oracle/lattice_oracle.py), the kick by the batch.py rule
+    (bench_wave.py's centre node when there is no defect)."""
+    from oracle import lattice_oracle as lo
+
+    kw = {} if spec.defect == "none" else dict(radius=spec.radius)
+    G, _, center = lo.build_case(spec.size, spec.dim, spec.layers, spec.defect, **kw)
+    nodes, rowptr, colidx, inv_mass, potential = lo.graph_arrays(G)
+    deg = np.diff(rowptr).astype(np.float64)
+    kick = spec.bench_kick_node() if spec.defect == "none" else lo.pick_kick_node(G, center, spec.dim)
+    u0 = np.zeros(len(nodes))
+    u0[nodes.index(kick)] = 1.0
+    return G, kick, rowptr, colidx, deg, inv_mass, potential, u0
+
+
+def _cfg5_point(job):
+    """One cfg5 grid point through the LITERAL pure-Python restatement of physics.py:106-129 (oracle.run_graph_python):
+    what one `run_wave_sim` call of the reference computes, minus networkx's dict lookups.  Runs in a worker process."""
+    radius, damping, dt = job
+    import tetrakis_sim_b200 as tk
+    from oracle import wave_oracle as wo
+
+    spec = tk.LatticeSpec(size=13, dim=3, layers=7, defect="blackhole", radius=radius)
+    _, _, rowptr, colidx, deg, inv_mass, potential, u0 = _literal_inputs(spec)
+    dt_eff, _, _ = wo.cfl_clamp(int(deg.max()), 1.0, dt, 50, damping)
+    t0 = time.perf_counter()
+    wo.run_graph_python(rowptr, colidx, deg, inv_mass, potential, u0, 50, dt_eff ** 2, damping)
+    return time.perf_counter() - t0, len(u0)
+
+
+def cpu_reference_tables(local, python_budget_visits=3e7):
+    """SURVEY.md 8(d)(i), as far as it can travel to the GPU box (the reference itself lives in /root/reference and does
+    not): the reference's seven published `scripts/bench_wave.py` sizes (benchmarks/bench_2d_after.csv, bench_3d_after.csv)
+    through (a) the drop-in run_wave_sim(G) on the networkx graph, wall clock, median of 3; (b) the literal per-edge
+    restatement in C on one core; (c) the literal restatement in pure Python on one core where it finishes in seconds --
+    and 2 x cores grid points of cfg5 (seed 0) through (c) on all host cores, one process each as
+    examples/naked_singularity_sweep.py does, extrapolated to the 65 536-point grid."""
+    import multiprocessing as mp
+    import statistics
+    import warnings
+    from concurrent.futures import ProcessPoolExecutor
+
+    import tetrakis_sim_b200 as tk
+    from oracle import wave_oracle as wo
+
+    rows = []
+    for dim, layers, size, steps in ((2, 1, 11, 50), (2, 1, 21, 50), (2, 1, 31, 50), (2, 1, 41, 50),
+                                     (3, 5, 7, 30), (3, 5, 11, 30), (3, 5, 15, 30)):
+        spec = tk.LatticeSpec(size=size, dim=dim, layers=layers)
+        G, kick, rowptr, colidx, deg, inv_mass, potential, u0 = _literal_inputs(spec)
+        dt_eff, _, _ = wo.cfl_clamp(int(deg.max()), 1.0, 0.1, steps, 0.0)
+        walls = []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            for _ in range(4):
+                t0 = time.perf_counter()
+                tk.run_wave_sim(G, steps=steps, initial_data={kick: 1.0}, c=1.0, dt=0.1, device=local)
+                walls.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        wo.run_graph(rowptr, colidx, deg, inv_mass, potential, u0, steps, dt_eff ** 2, 0.0)
+        t_c = time.perf_counter() - t0
+        row = {"dim": dim, "layers": layers, "size": size, "steps": steps, "nodes": len(u0), "edges": int(rowptr[-1]) // 2,
+               "dropin_wall_s_median": statistics.median(walls[1:]), "literal_c_1_core_s": t_c}
+        if rowptr[-1] * steps <= python_budget_visits:
+            t0 = time.perf_counter()
+            wo.run_graph_python(rowptr, colidx, deg, inv_mass, potential, u0, steps, dt_eff ** 2, 0.0)
+            row["literal_python_1_core_s"] = time.perf_counter() - t0
+        rows.append(row)
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    radii, damps, dts = np.linspace(0.5, 4.0, 64), np.linspace(0.0, 0.05, 32), np.linspace(0.02, 0.2, 32)
+    n_pts = min(64, 2 * cores)
+    jobs = [(float(radii[rng.integers(64)]), float(damps[rng.integers(32)]), float(dts[rng.integers(32)]))
+            for _ in range(n_pts)]
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+        res = list(ex.map(_cfg5_point, jobs))
+    wall = time.perf_counter() - t0
+    per_sim = statistics.mean(r[0] for r in res)
+    return {"bench_wave_sizes": rows,
+            "cfg5_points": {"points": n_pts, "seed": 0, "cores": cores, "wall_s": wall, "mean_s_per_simulation": per_sim,
+                            "node_updates": int(sum(r[1] for r in res)) * 50,
+                            "extrapolated_hours_for_65536": 65536 * per_sim / cores / 3600.0,
+                            "kind": "port (oracle.run_graph_python: the literal loop of physics.py:106-129 in pure Python, "
+                                    "one process per point)"},
+            "note": "the unmodified reference measured 0.0855 / 0.358 / 1.206 / 3.417 s (2-D) and 0.0697 / 0.2495 / 0.6938 s "
+                    "(3-D) for these sizes and 1.336 s per cfg5 simulation on this image's host (BASELINE.md section 2); it "
+                    "cannot travel to the GPU box"}
 
 
 def _csr_tetrakis(S, L):

@@ -1,7 +1,7 @@
 """Debug aid: the cross scheme against the oracle, errors split into cross cells / bulk cells."""
 import os, sys, warnings
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 os.environ["TK_FX_MIN_NODES"] = "0"
 os.environ["TK_FX_MAXFRAC"] = "95"
 import tetrakis_sim_b200 as tk

@@ -1,7 +1,7 @@
 """Debug aid: two slab plans on ONE GPU in lockstep with the in-kernel early arrival signal."""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import tetrakis_sim_b200 as tk
 from tetrakis_sim_b200.slab import CudaSlabBackend

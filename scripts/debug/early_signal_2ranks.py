@@ -1,6 +1,6 @@
 """Debug aid: 2 ranks, p2p transport with the in-kernel early signal, stack dump if it stalls."""
 import faulthandler, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch, torch.distributed as dist
 import tetrakis_sim_b200 as tk

@@ -577,3 +577,18 @@ def test_graphs_that_are_not_tetrakis_lattices_are_refused_by_the_structured_rou
         lattice_tables_from_graph(G)
     with pytest.raises(ValueError):
         lattice_tables_from_graph(nx.MultiGraph([((0, 0, "A"), (0, 0, "B"))]))
+
+
+def test_bench_cpu_reference_table_inputs():
+    """bench.py's CPU tables: the literal restatement runs on the graph the reference would build, kicked
+    where the reference's front-ends kick it."""
+    import bench
+
+    spec = tk.LatticeSpec(size=11, dim=3, layers=7, defect="blackhole", radius=2.5)
+    G, kick, rowptr, colidx, deg, inv_mass, potential, u0 = bench._literal_inputs(spec)
+    assert kick == spec.kick_node() == (3, 3, 3, "A") and len(u0) == spec.num_nodes == 3064
+    assert int(rowptr[-1]) // 2 == G.number_of_edges() == 35500 and u0.sum() == 1.0
+    seconds, nodes = bench._cfg5_point((2.5, 0.01, 0.1))
+    assert nodes == 4732 - 324 and seconds > 0.0
+    plain = tk.LatticeSpec(size=7, dim=2)
+    assert bench._literal_inputs(plain)[1] == plain.bench_kick_node()

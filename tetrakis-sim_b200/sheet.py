@@ -222,7 +222,7 @@ def bench_sheet(args, emit: bool = True, keep_pg: bool = False):
     import torch
     import torch.distributed as dist
 
-    from bench import METRIC, UNIT, ClockSampler, measured_peak_gbs
+    from bench import METRIC, UNIT, ClockSampler, measured_peak_gbs, ncu_traffic
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -328,7 +328,9 @@ def bench_sheet(args, emit: bool = True, keep_pg: bool = False):
                                       "sums + totals of two time levels) per pass",
                        "l2": "band state >> 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": 8.7853e9 * backend.plan.num_nodes / 268435456.0,  # ncu, scaled from the 8192^2 capture
+                         # ncu capture of the same kernel at the same K on the 8192^2 sheet, scaled to the band (or null)
+                         "traffic": (lambda t: None if t is None else t * backend.plan.num_nodes / 268435456.0)(
+                             ncu_traffic("cfg2-2d-8192-fused", max(passes))),
                          "peak_source": peak_src, "kernel": f"lat_fused2d_kernel (K={max(passes)}), rank 0's band",
                          "algorithmic_bytes_per_launch": pass_bytes, "bytes_per_update": 32.0 * len(passes) / args.steps,
                          "kernel_ms_per_launch": kms / max(kpasses, 1),

@@ -50,6 +50,9 @@ const char *tk_last_error(void);
 int tk_device_count(int *count);
 int tk_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major,
                    int *cc_minor, int64_t *total_mem_bytes);
+/* Sustained FP64 instruction rate and HBM bandwidth the pass-length heuristics of tk_plan_run assume for this device,
+ * derived from its attributes (SM count, clocks, bus width) and the efficiencies measured on a B200. */
+int tk_device_rates(int device, double *fp64_per_s, double *hbm_bytes_per_s);
 /* The library keeps freed device blocks of up to 256 MB (at most 2 GB per device) for reuse by later plans, because
  * driver allocation calls cost more than a small simulation; this returns them to the driver.  TK_DEV_CACHE=0
  * disables the cache. */

@@ -23,10 +23,12 @@ def _oracle(S, u0, up0, steps, coeff, damping, probes):
 
 
 def _default_kmax(S, damping):
-    """Mirror of csrc/host_fused.inc:fuse_choice: longer passes on sheets that are launch-bound."""
+    """Mirror of csrc/host_fused.inc:fuse_choice: longer passes on sheets that are launch-bound; the FP64 and HBM
+    rates are the ones the library derives from the device's attributes (tk_device_rates)."""
+    rates = tk.device_rates(0)
     ncell = float(S) * S
-    t_fp = ncell * (1.0 if damping == 0.0 else 2.0) * 16.4e-6 / 6.7e7
-    t_pass = ncell * 128.0 / 6.3e12 + 40e-6
+    t_fp = ncell * (4.0 if damping == 0.0 else 8.0) / rates["fp64_per_s"]
+    t_pass = ncell * 128.0 / rates["hbm_bytes_per_s"] + 40e-6
     k = int(0.6 * t_pass / t_fp)
     return max(48 if damping == 0.0 else 24, min(k, 1024)) // 8 * 8
 

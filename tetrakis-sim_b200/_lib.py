@@ -19,7 +19,7 @@ TK_OK, TK_ERR_INVALID, TK_ERR_CUDA, TK_ERR_NOMEM, TK_ERR_NO_DEVICE = 0, 1, 2, 3,
 
 # every symbol declared in include/tetrakis_b200.h (tests check the .so exports all of them)
 ABI_SYMBOLS = (
-    "tk_abi_version", "tk_last_error", "tk_device_count", "tk_device_info", "tk_device_trim",
+    "tk_abi_version", "tk_last_error", "tk_device_count", "tk_device_info", "tk_device_rates", "tk_device_trim",
     "tk_graph_plan_create", "tk_lattice_plan_create", "tk_lattice_plan_create_ex",
     "tk_plan_set_stream", "tk_plan_num_nodes", "tk_plan_max_degree",
     "tk_plan_set_state_sparse", "tk_plan_set_state", "tk_plan_get_state",
@@ -97,6 +97,7 @@ def lib():
     L.tk_device_info.argtypes = [c_int, c_char_p, c_int, POINTER(c_int), POINTER(c_int),
                                  POINTER(c_int), POINTER(c_int64)]  # fmt: skip
     L.tk_device_trim.argtypes = [c_int]
+    L.tk_device_rates.argtypes = [c_int, c_void_p, c_void_p]
     L.tk_graph_plan_create.argtypes = [c_int, c_int64, P, P, P, P, P, POINTER(P)]
     L.tk_lattice_plan_create.argtypes = [c_int, POINTER(LatticeDesc), POINTER(P)]
     L.tk_lattice_plan_create_ex.argtypes = [c_int, POINTER(LatticeDesc), ctypes.c_uint32, POINTER(P)]
@@ -177,6 +178,13 @@ def device_info(device: int = 0) -> dict:
                                ctypes.byref(mnr), ctypes.byref(mem)))  # fmt: skip
     return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value),
             "total_mem": mem.value}  # fmt: skip
+
+
+def device_rates(device: int = 0) -> dict:
+    """FP64 instructions / s and HBM bytes / s the pass-length heuristics assume for this device (tk_device_rates)."""
+    f, b = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    check(lib().tk_device_rates(device, ctypes.byref(f), ctypes.byref(b)))
+    return {"fp64_per_s": f.value, "hbm_bytes_per_s": b.value}
 
 
 def device_trim(device: int = 0) -> None:
@@ -474,5 +482,5 @@ def dft_abs(series, device: int = 0):
     return (spec[0], int(arg[0])) if single else (spec, arg)
 
 
-__all__ = ["Plan", "lib", "check", "device_count", "device_info", "dft_abs", "ABI_SYMBOLS",
+__all__ = ["Plan", "lib", "check", "device_count", "device_info", "device_rates", "dft_abs", "ABI_SYMBOLS",
            "BackendUnavailable", "NoDeviceError", "TkError", "c_uint8"]  # fmt: skip

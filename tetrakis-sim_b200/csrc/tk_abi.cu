@@ -137,6 +137,29 @@ int cached_sm_count(int device)
     return n;
 }
 
+// Sustained rates the pass-length heuristics are calibrated on, derived from the device's own attributes instead of
+// literals measured on one box: FP64 instructions per second = 0.88 x SMs x 64 lanes x SM clock (the fused passes reach
+// 88 % of the FP64 pipe: 16.4 us per step of 6.7e7 cells at 4 DFMA per cell on a 148-SM, 1 965 MHz B200), HBM bytes per
+// second = 0.82 x 2 x memory clock x bus width (6.3 TB/s of the 7.67 TB/s a B200 reports: 3 996 MHz, 7 680 bits).  Falls back to those B200
+// figures when an attribute is unavailable.
+struct DevRates { double fp64_per_s, hbm_bytes_per_s; };
+
+DevRates device_rates(int device)
+{
+    static DevRates cache[16] = {};
+    if (device >= 0 && device < 16 && cache[device].fp64_per_s > 0.0) return cache[device];
+    DevRates r{1.634e13, 6.3e12};
+    int clk_khz = 0, mem_khz = 0, bus_bits = 0;
+    const bool ok = cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, device) == cudaSuccess &&
+                    cudaDeviceGetAttribute(&mem_khz, cudaDevAttrMemoryClockRate, device) == cudaSuccess &&
+                    cudaDeviceGetAttribute(&bus_bits, cudaDevAttrGlobalMemoryBusWidth, device) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    if (ok && clk_khz > 0) r.fp64_per_s = 0.88 * cached_sm_count(device) * 64.0 * clk_khz * 1e3;
+    if (ok && mem_khz > 0 && bus_bits > 0) r.hbm_bytes_per_s = 0.82 * 2.0 * mem_khz * 1e3 * (bus_bits / 8.0);
+    if (device >= 0 && device < 16) cache[device] = r;
+    return r;
+}
+
 int fail(int code, const char *fmt, ...)
 {
     char buf[1024];

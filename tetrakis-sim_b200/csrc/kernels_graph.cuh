@@ -11,7 +11,7 @@
 
 namespace tk {
 
-template <bool KEN>
+template <bool KEN, bool PIPE = false>
 __global__ void __launch_bounds__(256)
 graph_step_kernel(long long n, const long long *__restrict__ slice_off,
                   const int *__restrict__ ell_idx, const double *__restrict__ deg,
@@ -29,13 +29,32 @@ graph_step_kernel(long long n, const long long *__restrict__ slice_off,
     const int *idx = ell_idx + off + lane;
     double nsum = 0.0;  // physics.py:115
     int k = 0;
-    for (; k + 4 <= width; k += 4) {  // gather 4 ahead, add strictly in order
-        const double a = u[idx[(size_t)k * 32]], b = u[idx[(size_t)(k + 1) * 32]];
-        const double c = u[idx[(size_t)(k + 2) * 32]], d = u[idx[(size_t)(k + 3) * 32]];
-        nsum = __dadd_rn(nsum, a);
-        nsum = __dadd_rn(nsum, b);
-        nsum = __dadd_rn(nsum, c);
-        nsum = __dadd_rn(nsum, d);
+    if (PIPE) {
+        // gather 4 ahead with the NEXT four indices already requested: the index stream (DRAM) and the gathers (cache)
+        // of consecutive groups overlap instead of alternating; the adds stay strictly in adjacency order
+        int j0 = 0, j1 = 0, j2 = 0, j3 = 0;
+        if (width >= 4) { j0 = idx[0]; j1 = idx[32]; j2 = idx[64]; j3 = idx[96]; }
+        for (; k + 4 <= width; k += 4) {
+            const int i0 = j0, i1 = j1, i2 = j2, i3 = j3;
+            if (k + 8 <= width) {
+                j0 = idx[(size_t)(k + 4) * 32]; j1 = idx[(size_t)(k + 5) * 32];
+                j2 = idx[(size_t)(k + 6) * 32]; j3 = idx[(size_t)(k + 7) * 32];
+            }
+            const double a = u[i0], b = u[i1], c = u[i2], d = u[i3];
+            nsum = __dadd_rn(nsum, a);
+            nsum = __dadd_rn(nsum, b);
+            nsum = __dadd_rn(nsum, c);
+            nsum = __dadd_rn(nsum, d);
+        }
+    } else {
+        for (; k + 4 <= width; k += 4) {  // gather 4 ahead, add strictly in order
+            const double a = u[idx[(size_t)k * 32]], b = u[idx[(size_t)(k + 1) * 32]];
+            const double c = u[idx[(size_t)(k + 2) * 32]], d = u[idx[(size_t)(k + 3) * 32]];
+            nsum = __dadd_rn(nsum, a);
+            nsum = __dadd_rn(nsum, b);
+            nsum = __dadd_rn(nsum, c);
+            nsum = __dadd_rn(nsum, d);
+        }
     }
     for (; k < width; ++k) nsum = __dadd_rn(nsum, u[idx[(size_t)k * 32]]);
     const double ui = u[i];

@@ -592,3 +592,28 @@ def test_bench_cpu_reference_table_inputs():
     assert nodes == 4732 - 324 and seconds > 0.0
     plain = tk.LatticeSpec(size=7, dim=2)
     assert bench._literal_inputs(plain)[1] == plain.bench_kick_node()
+
+
+def test_install_switches_the_structured_route(monkeypatch):
+    """install(structured=...) overrides TETRAKIS_B200_AUTO_STRUCTURED; uninstall() hands the choice back to the
+    environment."""
+    from tetrakis_sim_b200 import physics as ph
+
+    monkeypatch.delenv("TETRAKIS_B200_AUTO_STRUCTURED", raising=False)
+    assert not ph.auto_structured_enabled()
+    try:
+        tk.install(structured=True)
+        assert ph.auto_structured_enabled()
+        tk.install()  # None: leaves the earlier choice alone
+        assert ph.auto_structured_enabled()
+    finally:
+        tk.uninstall()
+    assert not ph.auto_structured_enabled()
+    monkeypatch.setenv("TETRAKIS_B200_AUTO_STRUCTURED", "1")
+    assert ph.auto_structured_enabled()
+    try:
+        tk.install(structured=False)
+        assert not ph.auto_structured_enabled()
+    finally:
+        tk.uninstall()
+    assert ph.auto_structured_enabled()

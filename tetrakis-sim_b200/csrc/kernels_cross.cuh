@@ -391,7 +391,8 @@ struct FxPipe {
     double mprev, mcur;  // level -1 at layers t-1, t
 };
 
-template <int K, bool UNDAMPED, int R, bool GUARD>
+// GUARD: bit 0 = mirror below the first layer (needed while t <= K), bit 1 = mirror above the last (needed from t >= L)
+template <int K, bool UNDAMPED, int R, int GUARD>
 __device__ __forceinline__ void fx_tick(FxPipe<K, UNDAMPED> &p, int t, int L, double lam, double cb, double coeff,
                                         double in0, double inm, double &outK, double &outK1)
 {
@@ -404,10 +405,11 @@ __device__ __forceinline__ void fx_tick(FxPipe<K, UNDAMPED> &p, int t, int L, do
         // level k at layer x = t - k from level k-1 at x-1, x, x+1 and level k-2 at x
         double a = p.w[k - 1][SA], b = p.w[k - 1][SB], c = p.w[k - 1][SN];
         const double prev = k >= 2 ? p.w[k - 2][SA] : p.mprev;
-        if (GUARD) {
-            const int x = t - k;
-            if (x <= 0) a = b;        // mirror below the first layer (uniform over the grid)
-            if (x >= L - 1) c = b;    // mirror above the last layer
+        if (GUARD & 1) {
+            if (t - k <= 0) a = b;        // mirror below the first layer (uniform over the grid)
+        }
+        if (GUARD & 2) {
+            if (t - k >= L - 1) c = b;    // mirror above the last layer
         }
         double n;
         if (UNDAMPED) n = fma(lam, b, -prev);
@@ -453,13 +455,18 @@ struct FxCtx {
     bool act;
 };
 
-// One tick.  R6 = t mod 6 picks the ring slot and (mod 3) the rotation of the pipeline windows at compile time.
-// STEADY: K < t < L - PD, i.e. every stage is away from the end layers, the tick loads, requests and stores.
-template <int K, bool UNDAMPED, int R6, bool STEADY>
-__device__ __forceinline__ void fx_bulk_tick(FxCtx<K, UNDAMPED> &c, int t)
+// One tick.  R3 = t mod 3 is the rotation of the pipeline windows (compile time: it indexes registers); slot = t mod 6 is
+// the ring slot (a constant in the unrolled steady loop, a run-time value elsewhere).
+// MODE 0 = STEADY: K < t < L - PD, i.e. every stage is away from the end layers, the tick loads, requests and stores.
+// MODE 1 / 2 / 3: guarded tick with the lower / upper / both end-layer mirrors (fx_tick GUARD bits); MODE 4: guarded tick
+// that needs no mirror (K < t < L, only the loads and stores are conditional).  The mirrors cost two selects per level
+// and side, so a tick pays only for the side it can reach.
+template <int K, bool UNDAMPED, int R3, int MODE>
+__device__ __forceinline__ void fx_bulk_tick(FxCtx<K, UNDAMPED> &c, int t, int slot)
 {
+    constexpr bool STEADY = MODE == 0;
     cp_async_wait<kFxPD - 1>();
-    unsigned char *s8 = c.r8 + R6 * kFxSlotBytes, *s16 = c.r16 + R6 * kFxSlotBytes;
+    unsigned char *s8 = c.r8 + slot * kFxSlotBytes, *s16 = c.r16 + slot * kFxSlotBytes;
     double na = *reinterpret_cast<const double *>(s8);
     double nb = *reinterpret_cast<const double *>(s8 + 256 * 8);
     const double2 yr = *reinterpret_cast<const double2 *>(s16);
@@ -481,7 +488,7 @@ __device__ __forceinline__ void fx_bulk_tick(FxCtx<K, UNDAMPED> &c, int t)
     cp_async_commit();
     const double h0 = hadamard4(na, c.m1, c.m2), hm = hadamard4(nb, c.m1, c.m2);
     double oK, oK1;
-    fx_tick<K, UNDAMPED, R6 % 3, !STEADY>(c.p, t, c.L, c.lam, c.cb, c.coeff, h0, hm, oK, oK1);
+    fx_tick<K, UNDAMPED, R3, (MODE == 0 || MODE == 4) ? 0 : MODE>(c.p, t, c.L, c.lam, c.cb, c.coeff, h0, hm, oK, oK1);
     if (STEADY || t >= K) {
         const double va = hadamard4(oK, c.m1, c.m2), vb = hadamard4(oK1, c.m1, c.m2);
         if (c.act) {  // .x = level K, .y = level K-1 (the host starts a pass on the slot that makes it so)
@@ -543,31 +550,46 @@ fx_bulk3d_kernel(const __grid_constant__ FxDev X, int halo, const double *in_a, 
         cp_async_commit();
     }
     const int nt = L + K;
-    auto guarded = [&](int t) {  // any tick, rotation picked at run time
-        switch (t % 6) {
-        case 0: fx_bulk_tick<K, UNDAMPED, 0, false>(x, t); break;
-        case 1: fx_bulk_tick<K, UNDAMPED, 1, false>(x, t); break;
-        case 2: fx_bulk_tick<K, UNDAMPED, 2, false>(x, t); break;
-        case 3: fx_bulk_tick<K, UNDAMPED, 3, false>(x, t); break;
-        case 4: fx_bulk_tick<K, UNDAMPED, 4, false>(x, t); break;
-        default: fx_bulk_tick<K, UNDAMPED, 5, false>(x, t); break;
+    auto guarded = [&](int t) {  // any tick: rotation and the mirrors it can reach picked at run time
+        const int slot = t % 6;
+        const int mode = (t <= K ? 1 : 0) | (t >= L ? 2 : 0);  // level k sits at layer t - k, k = 1 .. K
+        switch (mode * 3 + t % 3) {
+        case 0: fx_bulk_tick<K, UNDAMPED, 0, 4>(x, t, slot); break;
+        case 1: fx_bulk_tick<K, UNDAMPED, 1, 4>(x, t, slot); break;
+        case 2: fx_bulk_tick<K, UNDAMPED, 2, 4>(x, t, slot); break;
+        case 3: fx_bulk_tick<K, UNDAMPED, 0, 1>(x, t, slot); break;
+        case 4: fx_bulk_tick<K, UNDAMPED, 1, 1>(x, t, slot); break;
+        case 5: fx_bulk_tick<K, UNDAMPED, 2, 1>(x, t, slot); break;
+        case 6: fx_bulk_tick<K, UNDAMPED, 0, 2>(x, t, slot); break;
+        case 7: fx_bulk_tick<K, UNDAMPED, 1, 2>(x, t, slot); break;
+        case 8: fx_bulk_tick<K, UNDAMPED, 2, 2>(x, t, slot); break;
+        case 9: fx_bulk_tick<K, UNDAMPED, 0, 3>(x, t, slot); break;
+        case 10: fx_bulk_tick<K, UNDAMPED, 1, 3>(x, t, slot); break;
+        default: fx_bulk_tick<K, UNDAMPED, 2, 3>(x, t, slot); break;
         }
     };
     int t = 0;
     const int t_steady = (K + 1 + 5) / 6 * 6;  // first multiple of 6 above K
+    // prologue (guarded), steady loop, epilogue (guarded): ONE call site for the guarded ticks -- the twelve specialised
+    // bodies are inlined once, not once per loop (with two call sites the compiler stops inlining and the pipeline
+    // registers turn into a stack frame)
 #pragma unroll 1
-    for (; t < min(nt, t_steady); ++t) guarded(t);
+    for (int phase = 0; phase < 2; ++phase) {
+        const int t_end = phase == 0 ? min(nt, t_steady) : nt;
 #pragma unroll 1
-    for (; t + 6 <= L - kFxPD; t += 6) {
-        fx_bulk_tick<K, UNDAMPED, 0, true>(x, t);
-        fx_bulk_tick<K, UNDAMPED, 1, true>(x, t + 1);
-        fx_bulk_tick<K, UNDAMPED, 2, true>(x, t + 2);
-        fx_bulk_tick<K, UNDAMPED, 3, true>(x, t + 3);
-        fx_bulk_tick<K, UNDAMPED, 4, true>(x, t + 4);
-        fx_bulk_tick<K, UNDAMPED, 5, true>(x, t + 5);
+        for (; t < t_end; ++t) guarded(t);
+        if (phase == 0) {
+#pragma unroll 1
+            for (; t + 6 <= L - kFxPD; t += 6) {
+                fx_bulk_tick<K, UNDAMPED, 0, 0>(x, t, 0);
+                fx_bulk_tick<K, UNDAMPED, 1, 0>(x, t + 1, 1);
+                fx_bulk_tick<K, UNDAMPED, 2, 0>(x, t + 2, 2);
+                fx_bulk_tick<K, UNDAMPED, 0, 0>(x, t + 3, 3);
+                fx_bulk_tick<K, UNDAMPED, 1, 0>(x, t + 4, 4);
+                fx_bulk_tick<K, UNDAMPED, 2, 0>(x, t + 5, 5);
+            }
+        }
     }
-#pragma unroll 1
-    for (; t < nt; ++t) guarded(t);
     cp_async_wait<0>();
 }
 
